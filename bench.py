@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- SpectralMixingLayer fwd+bwd tokens/s on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f32|bf16] [--impl ours|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+              bench.py --gpus N --steps K --warmup W
+
+A "step" is one forward + one backward of the layer over one batch of synthetic input.  Workload at N=1 is
+BASELINE.json configs[1]: SpectralMixingLayer(embed_dim=768), x = (16, 8192, 768); weak scaling (each rank holds its
+own batch of 16, i.e. the batch axis is sharded) with one NCCL all-reduce(sum) of the filter/bias gradients per step.
+
+One JSON line on stdout (rank 0):
+  value        whole-job tokens/s (tokens = B*T summed over ranks), inputs resident in HBM, CUDA-event timed
+  e2e          same metric through the public module API with HOST (pinned) x and g copied in and y, gx and the filter
+               gradients copied back inside the timed region
+  roofline     dominant kernel (fused backward): algorithmic bytes / measured launch time vs MEASURED_PEAKS.json
+  cpu_baseline oracle torch port (same torch.fft algorithm as the reference) timed on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+METRIC = "spectral_mixing_fwd_bwd_tokens_per_sec"
+UNIT = "tokens/s"
+CFG = {"B": 16, "T": 8192, "D": 768}      # BASELINE.json configs[1]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=CFG["B"], help="per-GPU batch")
+    ap.add_argument("--seq", type=int, default=CFG["T"])
+    ap.add_argument("--embed", type=int, default=CFG["D"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's torch port (== the reference's torch.fft algorithm) on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(B, T, D, steps, warmup, budget_s=None):
+    from oracle import spectral_mixing_oracle as orc   # allowed here: cpu_baseline / --impl reference legs only
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen = torch.Generator().manual_seed(0)
+    Fn = D // 2
+    w_re, w_im, bias = torch.randn(D, Fn, generator=gen), torch.randn(D, Fn, generator=gen), torch.randn(D, generator=gen)
+    x, g = torch.randn(B, T, D, generator=gen), torch.randn(B, T, D, generator=gen)
+    for _ in range(warmup):
+        orc.torch_port_fwd_bwd(x, w_re, w_im, bias, g)
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        orc.torch_port_fwd_bwd(x, w_re, w_im, bias, g)
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_start > budget_s and len(times) >= 3:
+            break
+    return sum(times) / len(times), len(times), torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = min(args.cpu_sample_batch, args.batch)
+    T, D = args.seq, args.embed
+    dt, n, threads = cpu_reference_step_time(B, T, D, args.steps, max(1, min(args.warmup, 2)))
+    val = B * T / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"SpectralMixingLayer(embed_dim={D}) fwd+bwd, x=({args.batch},{T},{D}) fp32, k={min(D // 2, T // 2)}",
+                   "note": f"CPU arm: each step is a bounded sample of the workload, batch {B} of {args.batch} (columns are independent)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"oracle torch port (torch.fft, {torch.__config__.parallel_info().splitlines()[0]}), "
+                                   f"x=({B},{T},{D}) fwd+bwd, mean of {n} steps"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi fields through NVML)
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:   # pragma: no cover
+            self.err = str(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok and self.t.is_alive():
+            self.t.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from tensor_cuda_fft_b200 import SpectralMixingLayer, _native, allreduce_filter_grads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a GPU (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.lib()
+
+    B, T, D = args.batch, args.seq, args.embed
+    Fn = D // 2
+    k = min(Fn, T // 2)
+    dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    esz = 4 if args.dtype == "f32" else 2
+    io = _native.DTYPE_F32 if args.dtype == "f32" else _native.DTYPE_BF16
+    plan = _native.plan(B, T, D, Fn, io)
+
+    torch.manual_seed(0 + rank)
+    layer = SpectralMixingLayer(D).to(dev)
+    with torch.no_grad():
+        layer.weight_real.normal_()
+        layer.weight_imag.normal_()
+        layer.bias.normal_()
+    x = torch.randn(B, T, D, device=dev).to(dtype)
+    g = torch.randn(B, T, D, device=dev).to(dtype)
+
+    def step():
+        layer.zero_grad(set_to_none=True)
+        xr = x.requires_grad_(True)
+        y = layer(xr)
+        y.backward(g)
+        if world > 1:
+            allreduce_filter_grads([layer])     # one flat NCCL all-reduce(sum) of [gw_re | gw_im | gb]
+        gx = xr.grad
+        xr.grad = None
+        return y, gx
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events, max over ranks ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = _native.launch_count()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _native.launch_count() - n0
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = t.item()
+    ms_step = ms_total / args.steps
+    value = world * B * T / (ms_step * 1e-3)
+
+    # ---- per-kernel timing through the raw C ABI (events on the launching stream), for the roofline ----
+    stream = torch.cuda.current_stream().cuda_stream
+    wr, wi, bs = layer.weight_real.detach(), layer.weight_imag.detach(), layer.bias.detach()
+    y = torch.empty_like(x)
+    gx = torch.empty_like(x)
+    xlow = torch.empty(max(lib.sml_xlow_bytes(B, T, D, Fn), 8), dtype=torch.uint8, device=dev)
+    gwr, gwi, gb = torch.empty(D, Fn, device=dev), torch.empty(D, Fn, device=dev), torch.empty(D, device=dev)
+    ws_bytes = lib.sml_workspace_bytes(B, T, D, Fn, io)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+
+    def fwd():
+        _native.check(lib.sml_forward(x.data_ptr(), wr.data_ptr(), wi.data_ptr(), bs.data_ptr(), y.data_ptr(),
+                                      xlow.data_ptr(), B, T, D, Fn, io, stream))
+
+    def bwd():
+        _native.check(lib.sml_backward(g.data_ptr(), xlow.data_ptr(), wr.data_ptr(), wi.data_ptr(), gx.data_ptr(),
+                                       gwr.data_ptr(), gwi.data_ptr(), gb.data_ptr(), ws.data_ptr(), ws_bytes,
+                                       B, T, D, Fn, io, stream))
+
+    def time_kernel(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b in evs:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) for a, b in evs]
+        return sum(ts) / len(ts), min(ts)
+
+    nk = max(args.steps, 10)
+    fwd_ms, fwd_min = time_kernel(fwd, nk)
+    bwd_ms, bwd_min = time_kernel(bwd, nk)
+    peak, peak_src = load_peaks()
+    xlow_bytes = B * D * k * 8
+    param_bytes = (2 * D * Fn + D) * 4
+    bytes_fwd = 2 * B * T * D * esz + xlow_bytes + param_bytes
+    bytes_bwd = 2 * B * T * D * esz + xlow_bytes + 2 * param_bytes
+    bytes_step = 4 * B * T * D * esz     # the 4-pass floor (read x, write y, read g, write gx)
+
+    def roof(nbytes, ms):
+        ach = nbytes / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
+
+    roofline = roof(bytes_bwd, bwd_ms)
+    roofline.update({"kernel": "sml_fast_kernel<BWD> (fused analysis + Wirtinger filter-grad + synthesis)" if plan["path"] == "fast" else "generic kernels",
+                     "launch_ms": bwd_ms, "launch_ms_min": bwd_min, "algorithmic_bytes": bytes_bwd, "peak_source": peak_src})
+    roofline_fwd = roof(bytes_fwd, fwd_ms)
+    roofline_fwd.update({"kernel": "sml_fast_kernel<FWD>", "launch_ms": fwd_ms, "launch_ms_min": fwd_min, "algorithmic_bytes": bytes_fwd})
+    roofline_step = roof(bytes_step, ms_step)
+    roofline_step.update({"note": "4-pass floor bytes / whole fwd+bwd step time (includes host launch gaps and, at N>1, the all-reduce)"})
+
+    # ---- end to end through the public module API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(B, T, D, dtype=dtype).pin_memory()
+        gh = torch.empty(B, T, D, dtype=dtype).pin_memory()
+        xh.copy_(x)
+        gh.copy_(g)
+        yh = torch.empty(B, T, D, dtype=dtype).pin_memory()
+        gxh = torch.empty(B, T, D, dtype=dtype).pin_memory()
+        gradh = torch.empty(2 * D * Fn + D, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            layer.zero_grad(set_to_none=True)
+            xd = xh.to(dev, non_blocking=True).requires_grad_(True)
+            gd = gh.to(dev, non_blocking=True)
+            yd = layer(xd)
+            yd.backward(gd)
+            if world > 1:
+                allreduce_filter_grads([layer])
+            yh.copy_(yd.detach(), non_blocking=True)
+            gxh.copy_(xd.grad, non_blocking=True)
+            flat = torch.cat([layer.weight_real.grad.reshape(-1), layer.weight_imag.grad.reshape(-1), layer.bias.grad])
+            gradh.copy_(flat, non_blocking=True)
+
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        s1.record()
+        barrier()
+        ms = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        ms /= n_e2e
+        e2e = {"value": world * B * T / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * T * D * esz,
+               "d2h_bytes_per_step": 2 * B * T * D * esz + param_bytes, "ms_per_step": ms, "steps": n_e2e,
+               "api": "SpectralMixingLayer.forward + autograd backward; pinned host x,g in; y, gx, filter grads out"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Bs = min(args.cpu_sample_batch, B)
+        dt, n, threads = cpu_reference_step_time(Bs, T, D, steps=40, warmup=1, budget_s=12.0)
+        cpu = {"value": Bs * T / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"oracle torch port (torch.fft on host, {torch.__config__.parallel_info().splitlines()[0]}), "
+                         f"x=({Bs},{T},{D}) fp32 fwd+bwd (batch {Bs} of {B}; columns independent), mean of {n} steps",
+               "ms_per_step": dt * 1e3}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"SpectralMixingLayer(embed_dim={D}) fwd+bwd, x=({B},{T},{D}) per GPU, {args.dtype} I/O, fp32 math, "
+                                   f"k={k} live bins, randn x/g/filter, dropout 0 (BASELINE.json configs[1])",
+                       "global_batch": world * B, "seq_len": T, "embed_dim": D, "parallelism": f"batch-sharded x{world}",
+                       "plan": plan, "l2": f"inputs larger than L2 ({2 * B * T * D * esz / 1e6:.0f} MB read per step vs 126 MB), no flush",
+                       "collective": "none" if world == 1 else "1 NCCL all-reduce(sum) of [gw_re|gw_im|gb] per step"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_step": roofline_step,
+            "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference in this container (CPU).
+
+Run from the repo root:  python -m oracle.make_golden
+Needs /root/reference (not present on the GPU box -- the fixtures are committed instead).
+The reference module is loaded by file path so fft_tensor/__init__.py side effects are avoided
+(SURVEY.md D9).  TEST INFRASTRUCTURE -- see oracle/__init__.py.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF_ROOT = os.environ.get("SML_REFERENCE_ROOT", "/root/reference")
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def load_reference(name: str):
+    path = os.path.join(REF_ROOT, "fft_tensor", name + ".py")
+    spec = importlib.util.spec_from_file_location("_ref_" + name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# (tag, B, T, D, num_filters or None, param init, upstream-grad kind)
+LAYER_CASES = [
+    ("t512_d64_f128", 1, 512, 64, 128, "randn", "randn"),        # BASELINE cfg-1 band (k=128 of T=512), narrow D
+    ("pow2_t64_d32", 2, 64, 32, None, "randn", "randn"),
+    ("nonpow2_t100_d32", 3, 100, 32, None, "randn", "randn"),    # reference accepts any T
+    ("short_t16_d64", 2, 16, 64, None, "randn", "randn"),        # T//2 < num_filters -> zero grad columns
+    ("odd_d_t48_d7", 2, 48, 7, 3, "randn", "randn"),             # odd embed, tiny filter bank
+    ("nf_gt_half_t128_d16", 1, 128, 16, 100, "randn", "randn"),  # num_filters > T//2
+    ("t1024_d48_f24", 1, 1024, 48, None, "randn", "randn"),      # streamed fast path (R>1)
+    ("default_init_ysum", 2, 128, 256, None, "default", "ones"), # spectral_layers.py:288-299 known answer 256.0
+]
+
+
+def run_layer_case(ref_sl, tag, B, T, D, nf, init, gkind, seed):
+    gen = torch.Generator().manual_seed(seed)
+    layer = ref_sl.SpectralMixingLayer(D, num_filters=nf)
+    if init == "randn":
+        with torch.no_grad():
+            layer.weight_real.copy_(torch.randn(layer.weight_real.shape, generator=gen))
+            layer.weight_imag.copy_(torch.randn(layer.weight_imag.shape, generator=gen))
+            layer.bias.copy_(torch.randn(layer.bias.shape, generator=gen))
+    x = torch.randn(B, T, D, generator=gen).requires_grad_(True)
+    g = torch.randn(B, T, D, generator=gen) if gkind == "randn" else torch.ones(B, T, D)
+    y = layer(x)
+    y.backward(g)
+    return {
+        "x": x.detach().numpy(), "g": g.numpy(),
+        "w_re": layer.weight_real.detach().numpy(), "w_im": layer.weight_imag.detach().numpy(),
+        "bias": layer.bias.detach().numpy(),
+        "y": y.detach().numpy(), "gx": x.grad.numpy(),
+        "gw_re": layer.weight_real.grad.numpy(), "gw_im": layer.weight_imag.grad.numpy(),
+        "gb": layer.bias.grad.numpy(),
+        "num_filters": np.int64(layer.num_filters),
+    }
+
+
+def run_wirtinger_cases(ref_w, seed):
+    gen = torch.Generator().manual_seed(seed)
+    out = {}
+    # WirtingerGradient.apply on the broadcast shape used by WirtingerSpectralFilter (:192-194)
+    B, k, D = 3, 10, 6
+    xf = torch.complex(torch.randn(B, k, D, generator=gen), torch.randn(B, k, D, generator=gen)).requires_grad_(True)
+    w = torch.complex(torch.randn(1, k, D, generator=gen), torch.randn(1, k, D, generator=gen)).requires_grad_(True)
+    gup = torch.complex(torch.randn(B, k, D, generator=gen), torch.randn(B, k, D, generator=gen))
+    f = ref_w.WirtingerGradient.apply(xf, w)
+    f.backward(gup)
+    out.update(mul_x=xf.detach().numpy(), mul_w=w.detach().numpy(), mul_g=gup.numpy(),
+               mul_out=f.detach().numpy(), mul_gx=xf.grad.numpy(), mul_gw=w.grad.numpy())
+    # WirtingerSpectralFilter module (:145-203)
+    B, T, D, nf = 2, 24, 5, 9
+    filt = ref_w.WirtingerSpectralFilter(D, nf)
+    with torch.no_grad():
+        filt.weight.real.copy_(torch.randn(D, nf, generator=gen))
+        filt.weight.imag.copy_(torch.randn(D, nf, generator=gen))
+    xf = torch.complex(torch.randn(B, T, D, generator=gen), torch.randn(B, T, D, generator=gen)).requires_grad_(True)
+    gup = torch.complex(torch.randn(B, T, D, generator=gen), torch.randn(B, T, D, generator=gen))
+    o = filt(xf)
+    o.backward(gup)
+    out.update(filt_x=xf.detach().numpy(), filt_g=gup.numpy(),
+               filt_w_re=filt.weight.real.detach().numpy(), filt_w_im=filt.weight.imag.detach().numpy(),
+               filt_out=o.detach().numpy(), filt_gx=xf.grad.numpy(),
+               filt_gw_re=filt.weight.real.grad.numpy(), filt_gw_im=filt.weight.imag.grad.numpy())
+    return out
+
+
+def main():
+    if not os.path.isdir(REF_ROOT):
+        sys.exit(f"{REF_ROOT} not found: golden vectors can only be regenerated where the reference is mounted")
+    torch.set_num_threads(1)
+    os.makedirs(OUT_DIR, exist_ok=True)
+    ref_sl = load_reference("spectral_layers")
+    ref_w = load_reference("wirtinger_ops")
+    for i, case in enumerate(LAYER_CASES):
+        data = run_layer_case(ref_sl, *case, seed=1000 + i)
+        np.savez_compressed(os.path.join(OUT_DIR, f"layer_{case[0]}.npz"), **data)
+        print("wrote", case[0], {k: v.shape for k, v in data.items() if hasattr(v, "shape") and v.ndim})
+    # learnable=False (spectral_layers.py:62-66, :301-309): identity up to FFT round trip
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 96, 12, generator=gen)
+    lay = ref_sl.SpectralMixingLayer(12, learnable=False)
+    np.savez_compressed(os.path.join(OUT_DIR, "layer_nonlearnable.npz"), x=x.numpy(), y=lay(x).numpy(),
+                        n_params=np.int64(sum(p.numel() for p in lay.parameters())))
+    np.savez_compressed(os.path.join(OUT_DIR, "wirtinger.npz"), **run_wirtinger_cases(ref_w, seed=4242))
+    # parameter-count known answer, BENCHMARKS.md:86
+    n = sum(p.numel() for p in ref_sl.SpectralMixingLayer(256).parameters())
+    assert n == 65792, n
+    print("golden vectors written to", OUT_DIR)
+
+
+if __name__ == "__main__":
+    main()

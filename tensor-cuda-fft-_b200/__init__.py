@@ -1,0 +1,15 @@
+"""spectral-mix-b200: B200-native (sm_100a) SpectralMixingLayer forward/backward of FFT-Tensor.
+
+Public surface mirrors the reference modules ``fft_tensor.spectral_layers`` and ``fft_tensor.wirtinger_ops``.
+"""
+from . import _native
+from .spectral_layers import (HybridSpectralAttention, SpectralMLPBlock, SpectralMixingLayer, spectral_mix)
+from .wirtinger_ops import (ComplexParameter, WirtingerGradient, WirtingerSpectralFilter)
+from .distributed import allreduce_filter_grads, shard_batch
+
+__version__ = "0.1.0"
+__all__ = [
+    "SpectralMixingLayer", "SpectralMLPBlock", "HybridSpectralAttention", "spectral_mix",
+    "WirtingerGradient", "ComplexParameter", "WirtingerSpectralFilter",
+    "allreduce_filter_grads", "shard_batch",
+]

@@ -1,0 +1,110 @@
+"""ctypes binding of libspectral_mix_b200.so (C ABI in include/spectral_mix_b200.h).
+
+The library is the product: if it is missing or fails to load, every op raises -- there is no PyTorch or
+CPU fallback (the reference's "try-import, else warn and fall back" convention, fft_tensor/tensor.py:13-18,
+is deliberately NOT reproduced).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libspectral_mix_b200.so")
+CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
+
+DTYPE_F32 = 0
+DTYPE_BF16 = 1
+PATH_FAST = 1
+PATH_GENERIC = 2
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC_DIR], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise NativeLibraryError("building libspectral_mix_b200.so failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+def _declare(lib):
+    c_int, c_void_p, c_size_t, c_ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_longlong
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib.sml_abi_version.restype = c_int
+    lib.sml_abi_version.argtypes = []
+    lib.sml_last_error.restype = ctypes.c_char_p
+    lib.sml_last_error.argtypes = []
+    lib.sml_launch_count.restype = ctypes.c_ulonglong
+    lib.sml_launch_count.argtypes = []
+    lib.sml_plan.restype = c_int
+    lib.sml_plan.argtypes = [c_int, c_int, c_int, c_int, c_int, ip, ip, ip, ip]
+    lib.sml_xlow_bytes.restype = c_size_t
+    lib.sml_xlow_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.sml_workspace_bytes.restype = c_size_t
+    lib.sml_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
+    lib.sml_forward.restype = c_int
+    lib.sml_forward.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_void_p]
+    lib.sml_backward.restype = c_int
+    lib.sml_backward.argtypes = [c_void_p] * 9 + [c_size_t] + [c_int] * 5 + [c_void_p]
+    lib.sml_wirtinger_mul_forward.restype = c_int
+    lib.sml_wirtinger_mul_forward.argtypes = [c_void_p] * 3 + [c_ll, c_ll, c_void_p]
+    lib.sml_wirtinger_mul_backward.restype = c_int
+    lib.sml_wirtinger_mul_backward.argtypes = [c_void_p] * 5 + [c_ll, c_ll, c_void_p]
+    lib.sml_wirtinger_filter_forward.restype = c_int
+    lib.sml_wirtinger_filter_forward.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
+    lib.sml_wirtinger_filter_backward.restype = c_int
+    lib.sml_wirtinger_filter_backward.argtypes = [c_void_p] * 7 + [c_int] * 4 + [c_void_p]
+
+
+EXPORTED_SYMBOLS = (
+    "sml_abi_version", "sml_last_error", "sml_plan", "sml_xlow_bytes", "sml_workspace_bytes",
+    "sml_forward", "sml_backward",
+    "sml_wirtinger_mul_forward", "sml_wirtinger_mul_backward",
+    "sml_wirtinger_filter_forward", "sml_wirtinger_filter_backward",
+    "sml_launch_count",
+)
+
+
+def lib():
+    """Load (once) and return the native library; raises NativeLibraryError if it is not built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise NativeLibraryError(
+                        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        f"or `make -C {CSRC_DIR}`. There is no fallback path.")
+                try:
+                    handle = ctypes.CDLL(LIB_PATH)
+                except OSError as e:   # pragma: no cover
+                    raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+                _declare(handle)
+                _lib = handle
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError("spectral_mix_b200: " + lib().sml_last_error().decode("utf-8", "replace"))
+
+
+def plan(B: int, T: int, D: int, F: int, io_dtype: int = DTYPE_F32) -> dict:
+    path, M, R, k = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(lib().sml_plan(B, T, D, F, io_dtype, ctypes.byref(path), ctypes.byref(M), ctypes.byref(R), ctypes.byref(k)))
+    return {"path": "fast" if path.value == PATH_FAST else "generic", "M": M.value, "R": R.value, "k": k.value}
+
+
+def launch_count() -> int:
+    return int(lib().sml_launch_count())

@@ -1,0 +1,402 @@
+// sml_fast.cuh -- fused SpectralMixingLayer forward / backward kernels for sm_100a (power-of-two T).
+//
+// What one launch computes (reference: /root/reference/fft_tensor/spectral_layers.py:88-116 and the
+// autograd graph it implies, == /root/reference/fft_tensor/wirtinger_ops.py:53-82):
+//   FWD : y  = Re(ifft(lowpass_k(fft(x) * W))) + bias               (+ saves X_low = fft(x)[:, :k, :])
+//   BWD : gx = Re(ifft(lowpass_k(fft(g) * conj(W)))) ,  gW += (1/T) fft(g)[:k] * conj(X_low) ,  gb += sum g
+//
+// Algorithm.  Only |f| < k <= M/2 bins are live, so with T = R*M the length-T
+// transform is streamed as R passes of a length-M = NR*NR four-step FFT over the decimated rows
+// t = R*m + r.  Two real channels (d, d+1) ride in one complex sequence z = x_d + i x_{d+1}; the
+// two-sided band of z (2k-1 bins) is accumulated IN REGISTERS across passes:
+//     Z[fs] = sum_r W_T^{r fs} FFT_M(z[r::R])[fs mod M]
+// The spectral "mid phase" un-mixes the two channels (Hermitian split through warp shuffles), applies the
+// complex filter, and re-packs a band spectrum C whose inverse transform is y_d + i y_{d+1}; synthesis is
+// the exact transpose of analysis and writes each output row once.  HBM traffic = read x + write y
+// (+ 2k/T of that for X_low).
+//
+// Thread mappings (NT = NR*P threads, P channel pairs per CTA):
+//   time side  : tid -> (p = tid % P, m2 = tid / P)   rows m = NR*m1 + m2 ; coalesced 8*P-byte row segments
+//   freq side  : tid -> (f1 = tid % NR, p = tid / NR) bins f = f1 + NR*f2 ; partner bin -f is in the same warp
+// Global -> shared staging is TMA (cp.async.bulk.tensor.4d) double buffered over passes and tiles; the
+// kernel is persistent (one CTA per SM, static round-robin over (batch, channel-tile) work items).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sml_dft.cuh"
+
+namespace sml {
+
+struct FastParams {
+    void* out;             // y (FWD) or gx (BWD): (B,T,D) IO
+    const float* w_re;     // (D,F)
+    const float* w_im;     // (D,F)
+    const float* bias;     // (D,) or null            (FWD)
+    cf* xlow;              // (B,D,k) complex64: written by FWD (nullable) / read by BWD (nullable)
+    float* gw_re;          // (D,F) zero-initialised, accumulated with atomics (BWD, nullable)
+    float* gw_im;
+    float* gb;             // (D,)
+    const cf* gtab;        // W_T^n = exp(-2 pi i n / T), n < T
+    int B, T, D, F, k, R;  // R = T / M passes
+    int ntd;               // channel tiles = ceil(D / 2P)
+    int ntiles;            // B * ntd
+    float invT;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // bounded spin: a lost TMA completion becomes a trap (reported as a launch failure) instead of a hung GPU
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) __trap();
+    }
+}
+// 4-D tiled TMA load global -> shared, completion signalled on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// element I/O: one channel pair (d, d+1) <-> complex
+// ------------------------------------------------------------------------------------------------
+template <typename IO>
+struct PairIO;
+template <>
+struct PairIO<float> {
+    static __device__ __forceinline__ cf load_s(const float* p) {   // shared, 8-byte aligned
+        const float2 v = *reinterpret_cast<const float2*>(p);
+        return cf{v.x, v.y};
+    }
+    static __device__ __forceinline__ void store_g(float* p, cf v) {
+        *reinterpret_cast<float2*>(p) = make_float2(v.re, v.im);
+    }
+};
+template <>
+struct PairIO<__nv_bfloat16> {
+    static __device__ __forceinline__ cf load_s(const __nv_bfloat16* p) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+        return cf{v.x, v.y};
+    }
+    static __device__ __forceinline__ void store_g(__nv_bfloat16* p, cf v) {
+        *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.re, v.im);
+    }
+};
+
+template <int NR, int P, typename IO>
+struct FastCfg {
+    static constexpr int NT = NR * P;
+    static constexpr int M = NR * NR;
+    static constexpr int XS = NR + 1;    // exchange row stride (complex): odd -> conflict-free both ways
+    static constexpr int TS = NR + 2;    // twiddle row stride (complex): 16-byte aligned rows, 4-bank skew
+    static constexpr int NBUF = 2;       // TMA stages
+    static constexpr int BOXROWS = M < 256 ? M : 256;
+    static constexpr int NBOX = M / BOXROWS;
+    static constexpr uint32_t STAGE_BYTES = (uint32_t)M * 2u * P * sizeof(IO);
+    static constexpr size_t SMEM_BYTES = (size_t)NBUF * STAGE_BYTES + (size_t)NT * XS * sizeof(cf) +
+                                         2u * NR * TS * sizeof(cf) + 2u * NR * sizeof(cf) + NBUF * sizeof(uint64_t);
+    static constexpr int TWPT = (M + NT - 1) / NT;   // twiddle-table entries each thread rebuilds per pass
+};
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int NR, int KJ, int P, typename IO, bool BWD>
+__global__ void __launch_bounds__(NR* P, 1)
+    sml_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastParams prm) {
+    using C = FastCfg<NR, P, IO>;
+    constexpr int NT = C::NT, M = C::M, XS = C::XS, TS = C::TS, NBUF = C::NBUF;
+    constexpr int NJ = 2 * KJ;   // live f2 columns held per thread: [0,KJ) and [NR-KJ, NR)
+    static_assert(NJ <= NR, "band wider than the sub-transform");
+    static_assert(NT % 32 == 0 && 32 % NR == 0, "freq-side partner bin must live in the same warp");
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    IO* tbuf = reinterpret_cast<IO*>(smem);                                  // [NBUF][M][2P]
+    cf* xch = reinterpret_cast<cf*>(smem + (size_t)NBUF * C::STAGE_BYTES);   // [NT][XS]
+    cf* tw = xch + NT * XS;                                                  // [2][NR][TS]   W_T^{(R m2 + r) f1}
+    cf* cj = tw + 2 * NR * TS;                                               // [2][NR]       W_T^{NR r f2s}
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(cj + 2 * NR);               // [NBUF]
+
+    const int tid = threadIdx.x;
+    const int tp = tid % P, tm2 = tid / P;      // time-side mapping
+    const int ff1 = tid % NR, fp2 = tid / NR;   // freq-side mapping
+    const int R = prm.R, T = prm.T, D = prm.D;
+
+    const int my_ntiles = (prm.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_loads = my_ntiles * R;
+
+    auto issue_load = [&](int L) {   // thread 0 only
+        if (L >= total_loads) return;
+        const int it = L / R, r = L - it * R;
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int b = tile / prm.ntd, dt = tile - b * prm.ntd;
+        const int s = L % NBUF;
+        mbar_expect_tx(&mbar[s], C::STAGE_BYTES);
+#pragma unroll
+        for (int bx = 0; bx < C::NBOX; ++bx)
+            tma_load_4d(tbuf + (size_t)s * M * 2 * P + (size_t)bx * C::BOXROWS * 2 * P, &tmap, &mbar[s], dt * 2 * P, r,
+                        bx * C::BOXROWS, b);
+    };
+
+    // twiddle tables for the NEXT pass are fetched from the global W_T table early and parked in registers
+    cf twpre[C::TWPT];
+    cf cjpre = cf{1.f, 0.f};
+    auto tw_fetch = [&](int rn) {
+#pragma unroll
+        for (int i = 0; i < C::TWPT; ++i) {
+            const int idx = tid + i * NT;
+            if (idx < M) {
+                const int m2 = idx / NR, f1 = idx % NR;
+                const float2 w = __ldg(reinterpret_cast<const float2*>(prm.gtab) + (R * m2 + rn) * f1);
+                twpre[i] = cf{w.x, w.y};
+            }
+        }
+        if (tid < NR) {
+            const int f2s = tid < NR / 2 ? tid : tid - NR;
+            const float2 w = __ldg(reinterpret_cast<const float2*>(prm.gtab) + ((NR * rn * f2s) & (T - 1)));
+            cjpre = cf{w.x, w.y};
+        }
+    };
+    auto tw_store = [&](int slot) {
+#pragma unroll
+        for (int i = 0; i < C::TWPT; ++i) {
+            const int idx = tid + i * NT;
+            if (idx < M) tw[slot * NR * TS + (idx / NR) * TS + (idx % NR)] = twpre[i];
+        }
+        if (tid < NR) cj[slot * NR + tid] = cjpre;
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NBUF; ++s) mbar_init(&mbar[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NBUF; ++s) issue_load(s);
+    }
+    tw_fetch(0);
+    tw_store(0);
+    __syncthreads();
+
+    int L = 0;      // loads consumed so far
+    int slot = 0;   // twiddle slot of the current pass
+    IO* const outp = reinterpret_cast<IO*>(prm.out);
+
+    for (int it = 0; it < my_ntiles; ++it) {
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int b = tile / prm.ntd, dt = tile - b * prm.ntd;
+
+        cf acc[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[j] = cf{0.f, 0.f};
+
+        // ===================== analysis: R streamed passes, band accumulated in registers =====================
+        for (int r = 0; r < R; ++r) {
+            tw_fetch(r + 1 == R ? 0 : r + 1);
+            mbar_wait(&mbar[L % NBUF], (uint32_t)(L / NBUF) & 1u);
+            cf v[NR];
+            {
+                const IO* src = tbuf + (size_t)(L % NBUF) * M * 2 * P + tm2 * 2 * P + 2 * tp;
+#pragma unroll
+                for (int m1 = 0; m1 < NR; ++m1) v[m1] = PairIO<IO>::load_s(src + m1 * NR * 2 * P);
+            }
+            Dft<NR, -1>::run(v);   // over m1 -> f1
+            {
+                const float4* twr = reinterpret_cast<const float4*>(tw + slot * NR * TS + tm2 * TS);
+#pragma unroll
+                for (int h = 0; h < NR / 2; ++h) {
+                    const float4 q = twr[h];
+                    if (h > 0) v[2 * h] = cmul(v[2 * h], cf{q.x, q.y});
+                    v[2 * h + 1] = cmul(v[2 * h + 1], cf{q.z, q.w});
+                }
+            }
+            __syncthreads();   // (A) everyone is done with tbuf[L%NBUF], tw[slot] and last pass's xch reads
+            {
+                cf* xrow = xch + tid * XS;
+#pragma unroll
+                for (int f1 = 0; f1 < NR; ++f1) xrow[f1] = v[f1];
+            }
+            if (tid == 0) issue_load(L + NBUF);
+            tw_store(slot ^ 1);
+            __syncthreads();   // (B)
+#pragma unroll
+            for (int m2 = 0; m2 < NR; ++m2) v[m2] = xch[(m2 * P + fp2) * XS + ff1];
+            Dft<NR, -1>::run(v);   // over m2 -> f2   (outputs outside the band are dead code)
+            {
+                const cf* cjs = cj + slot * NR;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int f2 = j < KJ ? j : NR - NJ + j;
+                    const cf c = cjs[f2];
+                    acc[j].re = SML_FMA(v[f2].re, c.re, SML_FMA(-v[f2].im, c.im, acc[j].re));
+                    acc[j].im = SML_FMA(v[f2].re, c.im, SML_FMA(v[f2].im, c.re, acc[j].im));
+                }
+            }
+            slot ^= 1;
+            ++L;
+        }
+
+        // ===================== mid phase: un-mix the channel pair, filter, re-pack =====================
+        const int d0 = dt * 2 * P + 2 * fp2;   // freq-side channel pair
+        const bool pvalid = d0 < D;
+        {
+            const int lane = tid & 31;
+            const int src_lane = (lane & ~(NR - 1)) | ((NR - ff1) & (NR - 1));
+            cf part[NJ];   // value of the band at -fs
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int pj = NJ - 1 - j;
+                const int pj0 = (NJ - j) % NJ;
+                float pre = __shfl_sync(0xffffffffu, acc[pj].re, src_lane);
+                float pim = __shfl_sync(0xffffffffu, acc[pj].im, src_lane);
+                if (ff1 == 0) {
+                    pre = acc[pj0].re;
+                    pim = acc[pj0].im;
+                }
+                part[j] = cf{pre, pim};
+            }
+            const size_t wrow0 = (size_t)d0 * prm.F, wrow1 = wrow0 + prm.F;
+            const size_t xrow0 = ((size_t)b * D + d0) * prm.k, xrow1 = xrow0 + prm.k;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const bool pos = j < KJ;
+                const int fs = pos ? ff1 + NR * j : ff1 + NR * (j - NJ);
+                const int af = fs < 0 ? -fs : fs;
+                const bool live = pvalid && af < prm.k;
+                const cf zp = pos ? acc[j] : part[j];
+                const cf zm = pos ? part[j] : acc[j];
+                // Hermitian split: spectra of the two real channels at +af
+                const cf s0 = cf{0.5f * (zp.re + zm.re), 0.5f * (zp.im - zm.im)};
+                const cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
+                cf w0 = cf{0.f, 0.f}, w1 = cf{0.f, 0.f};
+                if (live) {
+                    w0 = cf{__ldg(prm.w_re + wrow0 + af), __ldg(prm.w_im + wrow0 + af)};
+                    w1 = cf{__ldg(prm.w_re + wrow1 + af), __ldg(prm.w_im + wrow1 + af)};
+                }
+                cf a0, a1;
+                if constexpr (!BWD) {
+                    if (pos && live && prm.xlow != nullptr) {
+                        reinterpret_cast<float2*>(prm.xlow)[xrow0 + af] = make_float2(s0.re, s0.im);
+                        reinterpret_cast<float2*>(prm.xlow)[xrow1 + af] = make_float2(s1.re, s1.im);
+                    }
+                    a0 = cmul(s0, w0);
+                    a1 = cmul(s1, w1);
+                } else {
+                    if (pos && live && prm.gw_re != nullptr) {
+                        const float2 x0 = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
+                        const float2 x1 = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
+                        const cf g0 = cmulc(s0, cf{x0.x, x0.y});   // G conj(X)
+                        const cf g1 = cmulc(s1, cf{x1.x, x1.y});
+                        atomicAdd(prm.gw_re + wrow0 + af, g0.re * prm.invT);
+                        atomicAdd(prm.gw_im + wrow0 + af, g0.im * prm.invT);
+                        atomicAdd(prm.gw_re + wrow1 + af, g1.re * prm.invT);
+                        atomicAdd(prm.gw_im + wrow1 + af, g1.im * prm.invT);
+                        if (fs == 0) {
+                            atomicAdd(prm.gb + d0, s0.re);
+                            atomicAdd(prm.gb + d0 + 1, s1.re);
+                        }
+                    }
+                    a0 = cmulc(s0, w0);   // G conj(W)
+                    a1 = cmulc(s1, w1);
+                }
+                cf c;
+                if (pos) {
+                    c = cf{0.5f * (a0.re - a1.im), 0.5f * (a0.im + a1.re)};
+                    if (j == 0 && ff1 == 0) c = cf{a0.re, a1.re};   // DC bin
+                } else {
+                    c = cf{0.5f * (a0.re + a1.im), 0.5f * (a1.re - a0.im)};
+                }
+                acc[j] = cf{c.re * prm.invT, c.im * prm.invT};
+            }
+        }
+
+        // ===================== synthesis: transpose of analysis, each output row written once =====================
+        const int td0 = dt * 2 * P + 2 * tp;   // time-side channel pair
+        float bias0 = 0.f, bias1 = 0.f;
+        if constexpr (!BWD) {
+            if (prm.bias != nullptr && td0 < D) {
+                bias0 = __ldg(prm.bias + td0);
+                bias1 = __ldg(prm.bias + td0 + 1);
+            }
+        }
+        for (int r = 0; r < R; ++r) {
+            tw_fetch(r + 1 == R ? 0 : r + 1);
+            cf v[NR];
+            {
+                const cf* cjs = cj + slot * NR;
+#pragma unroll
+                for (int f2 = 0; f2 < NR; ++f2) v[f2] = cf{0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int f2 = j < KJ ? j : NR - NJ + j;
+                    v[f2] = cmulc(acc[j], cjs[f2]);
+                }
+            }
+            Dft<NR, +1>::run(v);   // over f2 -> m2
+            {
+                const cf* twc = tw + slot * NR * TS + ff1;
+#pragma unroll
+                for (int m2 = 0; m2 < NR; ++m2) v[m2] = cmulc(v[m2], twc[m2 * TS]);
+            }
+            __syncthreads();   // (A') previous xch readers are done
+#pragma unroll
+            for (int m2 = 0; m2 < NR; ++m2) xch[(m2 * P + fp2) * XS + ff1] = v[m2];
+            tw_store(slot ^ 1);
+            __syncthreads();   // (B')
+            {
+                const cf* xrow = xch + tid * XS;
+#pragma unroll
+                for (int f1 = 0; f1 < NR; ++f1) v[f1] = xrow[f1];
+            }
+            Dft<NR, +1>::run(v);   // over f1 -> m1
+            if (td0 < D) {
+                IO* dst = outp + ((size_t)b * T + r + (size_t)R * tm2) * D + td0;
+                const size_t step = (size_t)R * NR * D;
+#pragma unroll
+                for (int m1 = 0; m1 < NR; ++m1)
+                    PairIO<IO>::store_g(dst + m1 * step, cf{v[m1].re + bias0, v[m1].im + bias1});
+            }
+            slot ^= 1;
+        }
+    }
+}
+
+}   // namespace sml

@@ -1,0 +1,195 @@
+"""B200-native drop-in for ``fft_tensor.spectral_layers`` (reference: /root/reference/fft_tensor/spectral_layers.py).
+
+Same classes, constructor signatures, parameter names/shapes and autograd behaviour; the forward and backward
+of ``SpectralMixingLayer`` run as ONE fused sm_100a kernel each (csrc/sml_fast.cuh) behind the C ABI in
+include/spectral_mix_b200.h.  CUDA only: a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native
+
+_IO_DTYPES = {torch.float32: _native.DTYPE_F32, torch.bfloat16: _native.DTYPE_BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream_handle(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _SpectralMixFn(torch.autograd.Function):
+    """y = Re(ifft(lowpass(fft(x) * W))) + bias, with the backward of spectral_layers.py:88-116
+    (== WirtingerGradient.backward, wirtinger_ops.py:53-82) computed by sml_backward."""
+
+    @staticmethod
+    def forward(ctx, x, w_re, w_im, bias):
+        if not x.is_cuda:
+            raise RuntimeError("SpectralMixingLayer (B200 build) needs a CUDA tensor; there is no CPU path")
+        if x.dtype not in _IO_DTYPES:
+            raise RuntimeError(f"Unsupported dtype {x.dtype}")   # reference raises on bf16; here fp32 and bf16 are I/O types
+        if x.dim() != 3:
+            raise RuntimeError(f"expected (B, T, D) input, got shape {tuple(x.shape)}")
+        B, T, D = x.shape
+        Fn = w_re.shape[1]
+        io = _IO_DTYPES[x.dtype]
+        lib = _native.lib()
+        xc = x.contiguous()
+        wr = w_re.detach().contiguous().float()
+        wi = w_im.detach().contiguous().float()
+        bs = None if bias is None else bias.detach().contiguous().float()
+        y = torch.empty_like(xc)
+        need_filter_grad = any(ctx.needs_input_grad[1:])
+        plan = _native.plan(B, T, D, Fn, io)
+        xlow = None
+        if need_filter_grad or plan["path"] == "generic":
+            nbytes = lib.sml_xlow_bytes(B, T, D, Fn)
+            xlow = torch.empty(max(nbytes // 8, 1), dtype=torch.complex64, device=x.device)
+        with torch.cuda.device(x.device):
+            _native.check(lib.sml_forward(_ptr(xc), _ptr(wr), _ptr(wi), _ptr(bs), _ptr(y), _ptr(xlow),
+                                          B, T, D, Fn, io, _stream_handle(x.device)))
+        ctx.save_for_backward(wr, wi, xlow if need_filter_grad else None)
+        ctx.shape = (B, T, D, Fn, io)
+        ctx.has_bias = bias is not None
+        ctx.param_dtypes = (w_re.dtype, w_im.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        wr, wi, xlow = ctx.saved_tensors
+        B, T, D, Fn, io = ctx.shape
+        lib = _native.lib()
+        gc = g.contiguous()
+        if gc.dtype != (torch.float32 if io == _native.DTYPE_F32 else torch.bfloat16):
+            gc = gc.to(torch.float32 if io == _native.DTYPE_F32 else torch.bfloat16)
+        gx = torch.empty_like(gc)
+        want = xlow is not None
+        flat = None
+        gwr = gwi = gb = None
+        if want:
+            # one flat buffer [gw_re | gw_im | gb] so a data-parallel job can all-reduce it in a single call
+            flat = torch.empty(2 * D * Fn + D, dtype=torch.float32, device=gc.device)
+            gwr = flat[: D * Fn].view(D, Fn)
+            gwi = flat[D * Fn: 2 * D * Fn].view(D, Fn)
+            gb = flat[2 * D * Fn:]
+        ws_bytes = lib.sml_workspace_bytes(B, T, D, Fn, io)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gc.device) if ws_bytes else None
+        with torch.cuda.device(gc.device):
+            _native.check(lib.sml_backward(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gx), _ptr(gwr), _ptr(gwi),
+                                           _ptr(gb), _ptr(ws), ws_bytes, B, T, D, Fn, io, _stream_handle(gc.device)))
+        need = ctx.needs_input_grad
+        dt = ctx.param_dtypes
+        return (gx if need[0] else None,
+                gwr.to(dt[0]) if (want and need[1]) else None,
+                gwi.to(dt[1]) if (want and need[2]) else None,
+                gb.to(dt[2]) if (want and ctx.has_bias and need[3]) else None)
+
+
+def spectral_mix(x: torch.Tensor, weight_real: torch.Tensor, weight_imag: torch.Tensor,
+                 bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Functional form of the fused layer (no dropout)."""
+    return _SpectralMixFn.apply(x, weight_real, weight_imag, bias)
+
+
+class SpectralMixingLayer(nn.Module):
+    """Drop-in for ``fft_tensor.spectral_layers.SpectralMixingLayer`` (spectral_layers.py:19-132).
+
+    FFT along the sequence axis, learnable complex low-pass filter on the first
+    ``k = min(num_filters, T // 2)`` bins (everything else is zeroed), inverse FFT, real part, + bias, dropout.
+    Parameters: ``weight_real``/``weight_imag`` of shape (embed_dim, num_filters), ``bias`` (embed_dim,) -- the
+    reference's state_dict loads unchanged.
+    """
+
+    def __init__(self, embed_dim: int, num_filters: Optional[int] = None, dropout: float = 0.0,
+                 learnable: bool = True):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_filters = num_filters or (embed_dim // 2)
+        self.learnable = learnable
+        if learnable:
+            self.weight_real = nn.Parameter(torch.ones(embed_dim, self.num_filters))
+            self.weight_imag = nn.Parameter(torch.zeros(embed_dim, self.num_filters))
+            self.bias = nn.Parameter(torch.zeros(embed_dim))
+        else:
+            self.register_parameter("weight_real", None)
+            self.register_parameter("weight_imag", None)
+            self.register_parameter("bias", None)
+        self.dropout = nn.Dropout(dropout)
+        self._verify_gradients = True
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, T, D = x.shape
+        assert D == self.embed_dim, f"Expected embed_dim={self.embed_dim}, got {D}"
+        if self.learnable and self.weight_real is not None:
+            y = _SpectralMixFn.apply(x, self.weight_real, self.weight_imag, self.bias)
+        else:
+            # learnable=False is fft followed by ifft(.).real (spectral_layers.py:88, :112): the identity up to
+            # rounding (reference self-test :301-309 measures 1.2e-7); returned exactly, as a new tensor.
+            if not x.is_cuda:
+                raise RuntimeError("SpectralMixingLayer (B200 build) needs a CUDA tensor; there is no CPU path")
+            y = x.clone()
+        return self.dropout(y)
+
+    def verify_energy_preservation(self, x: torch.Tensor, y: torch.Tensor) -> float:
+        """sum(y^2) / (sum(x^2) + 1e-8), spectral_layers.py:122-132."""
+        energy_in = torch.sum(x.float() ** 2).item()
+        energy_out = torch.sum(y.float() ** 2).item()
+        return energy_out / (energy_in + 1e-8)
+
+
+class SpectralMLPBlock(nn.Module):
+    """x + spectral_mix(norm1(x)); x + mlp(norm2(x))  -- spectral_layers.py:135-190 (the layer's main caller)."""
+
+    def __init__(self, embed_dim: int, mlp_ratio: int = 4, dropout: float = 0.1):
+        super().__init__()
+        self.spectral_mix = SpectralMixingLayer(embed_dim=embed_dim, dropout=dropout, learnable=True)
+        self.norm1 = nn.LayerNorm(embed_dim)
+        self.norm2 = nn.LayerNorm(embed_dim)
+        hidden_dim = embed_dim * mlp_ratio
+        self.mlp = nn.Sequential(
+            nn.Linear(embed_dim, hidden_dim),
+            nn.GELU(),
+            nn.Dropout(dropout),
+            nn.Linear(hidden_dim, embed_dim),
+            nn.Dropout(dropout),
+        )
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = x + self.spectral_mix(self.norm1(x))
+        x = x + self.mlp(self.norm2(x))
+        return x
+
+
+class HybridSpectralAttention(nn.Module):
+    """Spectral mixing + (full) softmax attention over the mixed stream -- spectral_layers.py:193-256."""
+
+    def __init__(self, embed_dim: int, num_heads: int = 8, window_size: int = 64, dropout: float = 0.1):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.spectral = SpectralMixingLayer(embed_dim, dropout=dropout)
+        self.qkv = nn.Linear(embed_dim, 3 * embed_dim)
+        self.proj = nn.Linear(embed_dim, embed_dim)
+        self.dropout = nn.Dropout(dropout)
+        self.norm = nn.LayerNorm(embed_dim)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, T, D = x.shape
+        H = self.num_heads
+        global_context = self.spectral(x)
+        qkv = self.qkv(self.norm(x + global_context)).reshape(B, T, 3, H, D // H).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        attn = F.softmax((q @ k.transpose(-2, -1)) / math.sqrt(D // H), dim=-1)
+        attn = self.dropout(attn)
+        out = (attn @ v).transpose(1, 2).reshape(B, T, D)
+        out = self.dropout(self.proj(out))
+        return x + out

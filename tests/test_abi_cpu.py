@@ -1,0 +1,103 @@
+"""No-GPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/spectral_mix_b200.h declares, and its host-side planning logic is right.  No compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    import __graft_entry__ as ge
+    from tensor_cuda_fft_b200 import _native
+    if not os.path.exists(_native.LIB_PATH):
+        ge.build()
+    return _native
+
+
+def test_header_symbols_exported(native):
+    hdr = open(os.path.join(ROOT, "include", "spectral_mix_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sml_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(native.EXPORTED_SYMBOLS)
+    raw = ctypes.CDLL(native.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+    assert native.lib().sml_abi_version() == 1
+
+
+def test_plan_selection(native):
+    p = native.plan(16, 8192, 768, 384)
+    assert p == {"path": "fast", "M": 1024, "R": 8, "k": 384}
+    assert native.plan(8, 512, 256, 128) == {"path": "fast", "M": 256, "R": 2, "k": 128}
+    assert native.plan(64, 4096, 1024, 512) == {"path": "fast", "M": 1024, "R": 4, "k": 512}
+    assert native.plan(1, 131072, 1024, 512)["R"] == 128
+    assert native.plan(3, 100, 32, 16)["path"] == "generic"      # non power-of-two T
+    assert native.plan(2, 48, 7, 3)["path"] == "generic"         # odd D
+    assert native.plan(2, 16, 64, 32)["k"] == 8                  # k = min(F, T//2)
+    assert native.plan(2, 16, 64, 32)["path"] == "generic"       # sub-transform would not fit in T
+    assert native.plan(2, 64, 32, 16) == {"path": "fast", "M": 64, "R": 1, "k": 16}
+    assert native.plan(16, 8192, 768, 384, native.DTYPE_BF16)["path"] == "fast"
+
+
+def test_buffer_sizes(native):
+    lib = native.lib()
+    assert lib.sml_xlow_bytes(16, 8192, 768, 384) == 16 * 768 * 384 * 8
+    assert lib.sml_workspace_bytes(16, 8192, 768, 384, 0) == 0
+    assert lib.sml_workspace_bytes(3, 100, 32, 16, 0) == 3 * 32 * 16 * 8
+    assert lib.sml_xlow_bytes(2, 1, 4, 2) == 0
+
+
+def test_bad_arguments_report_errors(native):
+    with pytest.raises(RuntimeError, match="invalid shape"):
+        native.plan(0, 8, 8, 4)
+    with pytest.raises(RuntimeError, match="io_dtype"):
+        native.plan(1, 8, 8, 4, 7)
+
+
+def test_module_surface_matches_reference():
+    from tensor_cuda_fft_b200 import SpectralMixingLayer, SpectralMLPBlock, HybridSpectralAttention
+    from tensor_cuda_fft_b200 import ComplexParameter, WirtingerSpectralFilter
+    layer = SpectralMixingLayer(256)
+    assert sum(p.numel() for p in layer.parameters()) == 65792          # BENCHMARKS.md:86
+    assert list(layer.state_dict().keys()) == ["weight_real", "weight_imag", "bias"]
+    assert layer.weight_real.shape == (256, 128) and layer.num_filters == 128
+    assert torch.all(layer.weight_real == 1) and torch.all(layer.weight_imag == 0) and torch.all(layer.bias == 0)
+    assert layer._verify_gradients is True and isinstance(layer.dropout, torch.nn.Dropout)
+    frozen = SpectralMixingLayer(64, learnable=False)
+    assert len(list(frozen.parameters())) == 0 and frozen.weight_real is None and frozen.bias is None
+    assert SpectralMixingLayer(64, num_filters=5, dropout=0.25).dropout.p == 0.25
+    blk = SpectralMLPBlock(64)
+    assert blk.spectral_mix.dropout.p == 0.1 and blk.mlp[0].out_features == 256
+    assert HybridSpectralAttention(64).spectral.embed_dim == 64
+    assert ComplexParameter((4, 3), "ones")().dtype == torch.complex64
+    assert WirtingerSpectralFilter(8, 3).weight.real.shape == (8, 3)
+    with pytest.raises(ValueError):
+        ComplexParameter((2, 2), "nope")
+
+
+def test_no_cpu_fallback():
+    from tensor_cuda_fft_b200 import SpectralMixingLayer, WirtingerGradient
+    layer = SpectralMixingLayer(8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layer(torch.randn(1, 4, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        SpectralMixingLayer(8, learnable=False)(torch.randn(1, 4, 8))
+    with pytest.raises(AssertionError, match="Expected embed_dim=8, got 6"):
+        layer(torch.randn(1, 4, 6))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        WirtingerGradient.apply(torch.randn(2, 3, dtype=torch.complex64), torch.randn(1, 3, dtype=torch.complex64))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "tensor-cuda-fft-_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,63 @@
+"""world_size-2 gloo test of the batch-sharding plumbing (no GPU): shard_batch partitions the batch and one flat
+all-reduce of [weight_real.grad | weight_imag.grad | bias.grad] reproduces the single-process gradient sum."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tensor_cuda_fft_b200.distributed import allreduce_filter_grads, shard_batch
+
+    class Fake(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.weight_real = torch.nn.Parameter(torch.zeros(4, 3))
+            self.weight_imag = torch.nn.Parameter(torch.zeros(4, 3))
+            self.bias = torch.nn.Parameter(torch.zeros(4))
+
+    gen = torch.Generator().manual_seed(0)
+    full = torch.randn(5, 7, 4, generator=gen)           # ragged: 5 samples over 2 ranks -> 3 + 2
+    mine = shard_batch(full, rank, world)
+    m = Fake()
+    # a stand-in "local gradient" that is a sum over the local batch
+    m.weight_real.grad = mine.sum(dim=(0, 1)).unsqueeze(1).repeat(1, 3)
+    m.weight_imag.grad = 2 * m.weight_real.grad
+    m.bias.grad = mine.sum(dim=(0, 1))
+    allreduce_filter_grads([m])
+    q.put((rank, mine.shape[0], m.weight_real.grad.clone(), m.weight_imag.grad.clone(), m.bias.grad.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_filter_grad_allreduce():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    gen = torch.Generator().manual_seed(0)
+    full = torch.randn(5, 7, 4, generator=gen)
+    want_b = full.sum(dim=(0, 1))
+    assert [r[1] for r in res] == [3, 2]
+    for _, _, gwr, gwi, gb in res:
+        assert torch.allclose(gb, want_b, atol=1e-5)
+        assert torch.allclose(gwr, want_b.unsqueeze(1).repeat(1, 3), atol=1e-5)
+        assert torch.allclose(gwi, 2 * want_b.unsqueeze(1).repeat(1, 3), atol=1e-5)

@@ -1,0 +1,334 @@
+"""GPU parity tests proper: the CUDA path (through the module API and through the raw C ABI) against
+ (1) the committed golden vectors produced by the unmodified reference,
+ (2) the oracle's torch port / float64 closed form on seeded inputs,
+ (3) size-independent properties at BASELINE.json's full sizes.
+Tolerance (BASELINE.json north_star): rel-L2 <= 1e-5 for fp32, <= 1e-2 for bf16 I/O."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spectral_mixing_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-2
+
+GOLDEN = sorted(f for f in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "layer_*.npz"))
+                if "nonlearnable" not in f)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import tensor_cuda_fft_b200 as p
+    from tensor_cuda_fft_b200 import _native
+    _native.lib()   # must load: no fallback
+    return p
+
+
+def make_layer(pkg, D, F, w_re, w_im, bias, dev):
+    layer = pkg.SpectralMixingLayer(D, num_filters=F)
+    with torch.no_grad():
+        layer.weight_real.copy_(torch.as_tensor(w_re))
+        layer.weight_imag.copy_(torch.as_tensor(w_im))
+        layer.bias.copy_(torch.as_tensor(bias))
+    return layer.to(dev)
+
+
+def run_layer(layer, x, g, dev, dtype=torch.float32):
+    xg = x.to(dev, dtype).requires_grad_(True)
+    y = layer(xg)
+    y.backward(g.to(dev, dtype))
+    torch.cuda.synchronize()
+    return [t.detach().float().cpu().numpy() for t in
+            (y, xg.grad, layer.weight_real.grad, layer.weight_imag.grad, layer.bias.grad)]
+
+
+NAMES = ("y", "gx", "gw_re", "gw_im", "gb")
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[6:-4] for p in GOLDEN])
+def test_golden_vectors(pkg, dev, path):
+    z = np.load(path)
+    B, T, D = z["x"].shape
+    F = int(z["num_filters"])
+    layer = make_layer(pkg, D, F, z["w_re"], z["w_im"], z["bias"], dev)
+    got = run_layer(layer, torch.from_numpy(z["x"]), torch.from_numpy(z["g"]), dev)
+    for name, a in zip(NAMES, got):
+        err = orc.rel_l2(a, z[name])
+        assert err <= TOL_F32, (name, err)
+    k = min(F, T // 2)
+    assert np.all(got[2][:, k:] == 0) and np.all(got[3][:, k:] == 0)    # dense zero columns >= k
+
+
+def test_known_answer_grad_norm(pkg, dev):
+    # spectral_layers.py:288-299 at default init: ||x.grad|| = sqrt(B*T*D) = 256
+    layer = pkg.SpectralMixingLayer(256).to(dev)
+    x = torch.randn(2, 128, 256, device=dev, requires_grad=True)
+    layer(x).sum().backward()
+    assert abs(x.grad.norm().item() - 256.0) < 1e-2
+    assert torch.isfinite(x.grad).all()
+
+
+SHAPES = [
+    # B, T, D, F(None=D//2)     expected path
+    (2, 64, 32, None, "fast"),          # M=64, R=1
+    (3, 256, 64, None, "fast"),         # M=64, R=4
+    (2, 512, 256, None, "fast"),        # cfg-1 geometry: M=256, R=2
+    (2, 256, 256, None, "fast"),        # k = M/2 edge
+    (1, 1024, 768, None, "fast"),       # M=1024, R=1, KJ=12
+    (2, 2048, 96, 384, "fast"),         # M=1024, R=2, channel tile tail (96 = 6 tiles of 16)
+    (1, 4096, 64, 512, "fast"),         # cfg-3 band: k=512, KJ=16
+    (1, 2048, 40, 200, "fast"),         # D not a multiple of the channel tile, KJ=8 variant
+    (2, 1024, 36, 300, "fast"),         # D % 16 = 4
+    (1, 8192, 32, 384, "fast"),         # cfg-2 column geometry: M=1024, R=8
+    (2, 384, 48, None, "generic"),      # non power-of-two T
+    (2, 77, 10, 5, "generic"),          # odd T
+    (2, 128, 30, None, "generic"),      # D*4 % 16 != 0
+    (1, 512, 768, None, "generic"),     # 2k = T < 1024: sub-transform does not fit
+    (2, 1, 8, 4, "generic"),            # T = 1 -> k = 0: y = bias
+    (1, 2, 6, 4, "generic"),            # T = 2 -> k = 1 (DC only)
+]
+
+
+@pytest.mark.parametrize("B,T,D,F,path", SHAPES)
+def test_random_shapes_vs_oracle(pkg, dev, B, T, D, F, path):
+    from tensor_cuda_fft_b200 import _native
+    Fn = F or D // 2
+    assert _native.plan(B, T, D, Fn)["path"] == path
+    gen = torch.Generator().manual_seed(B * 7919 + T * 31 + D)
+    w_re, w_im, bias = (torch.randn(D, Fn, generator=gen), torch.randn(D, Fn, generator=gen), torch.randn(D, generator=gen))
+    x, g = torch.randn(B, T, D, generator=gen), torch.randn(B, T, D, generator=gen)
+    want = orc.closed_form_f64(x.numpy(), w_re.numpy(), w_im.numpy(), bias.numpy(), g.numpy())
+    layer = make_layer(pkg, D, Fn, w_re, w_im, bias, dev)
+    got = run_layer(layer, x, g, dev)
+    for name, a in zip(NAMES, got):
+        err = orc.rel_l2(a, want[name])
+        assert err <= TOL_F32, (name, err)
+    k = want["k"]
+    assert np.all(got[2][:, k:] == 0) and np.all(got[3][:, k:] == 0)
+
+
+@pytest.mark.parametrize("B,T,D", [(2, 2048, 96), (2, 512, 256), (1, 8192, 64), (2, 100, 32)])
+def test_bf16_io(pkg, dev, B, T, D):
+    # the reference rejects bf16: oracle = fp32 reference on bf16-rounded inputs
+    gen = torch.Generator().manual_seed(T + D)
+    Fn = D // 2
+    w_re, w_im, bias = (torch.randn(D, Fn, generator=gen), torch.randn(D, Fn, generator=gen), torch.randn(D, generator=gen))
+    x = torch.randn(B, T, D, generator=gen).bfloat16().float()
+    g = torch.randn(B, T, D, generator=gen).bfloat16().float()
+    want = orc.closed_form_f64(x.numpy(), w_re.numpy(), w_im.numpy(), bias.numpy(), g.numpy())
+    layer = make_layer(pkg, D, Fn, w_re, w_im, bias, dev)
+    got = run_layer(layer, x, g, dev, torch.bfloat16)
+    for name, a in zip(NAMES, got):
+        err = orc.rel_l2(a, want[name])
+        assert err <= TOL_BF16, (name, err)
+
+
+def test_nonlearnable_identity_and_no_grad(pkg, dev, golden_dir):
+    z = np.load(os.path.join(golden_dir, "layer_nonlearnable.npz"))
+    layer = pkg.SpectralMixingLayer(12, learnable=False).to(dev)
+    x = torch.from_numpy(z["x"]).to(dev).requires_grad_(True)
+    y = layer(x)
+    assert orc.rel_l2(y.detach().cpu().numpy(), z["y"]) < 1e-6
+    y.sum().backward()
+    assert torch.all(x.grad == 1)
+    lay2 = pkg.SpectralMixingLayer(32).to(dev)
+    with torch.no_grad():
+        out = lay2(torch.randn(2, 64, 32, device=dev))
+    assert not out.requires_grad
+    assert abs(lay2.verify_energy_preservation(out, out) - 1.0) < 1e-6
+
+
+def test_grad_accumulates_and_frozen_filter(pkg, dev):
+    gen = torch.Generator().manual_seed(3)
+    layer = pkg.SpectralMixingLayer(64).to(dev)
+    x = torch.randn(2, 256, 64, generator=gen).to(dev)
+    layer(x).sum().backward()
+    g1 = layer.bias.grad.clone()
+    layer(x).sum().backward()
+    assert torch.allclose(layer.bias.grad, 2 * g1, rtol=1e-5)
+    for p in layer.parameters():
+        p.requires_grad_(False)
+    xr = x.clone().requires_grad_(True)
+    layer(xr).sum().backward()     # gx only: no xlow saved, no filter grads
+    assert xr.grad is not None and torch.isfinite(xr.grad).all()
+
+
+def test_state_dict_roundtrip_from_reference_layout(pkg, dev, golden_dir):
+    z = np.load(os.path.join(golden_dir, "layer_pow2_t64_d32.npz"))
+    sd = {"weight_real": torch.from_numpy(z["w_re"]), "weight_imag": torch.from_numpy(z["w_im"]),
+          "bias": torch.from_numpy(z["bias"])}
+    layer = pkg.SpectralMixingLayer(32)
+    layer.load_state_dict(sd, strict=True)
+    y = layer.to(dev)(torch.from_numpy(z["x"]).to(dev))
+    assert orc.rel_l2(y.detach().cpu().numpy(), z["y"]) <= TOL_F32
+
+
+def test_dropout_and_block_run(pkg, dev):
+    torch.manual_seed(0)
+    blk = pkg.SpectralMLPBlock(64).to(dev)
+    x = torch.randn(2, 128, 64, device=dev, requires_grad=True)
+    blk(x).sum().backward()
+    assert torch.isfinite(x.grad).all() and blk.spectral_mix.weight_imag.grad is not None
+    blk.eval()
+    with torch.no_grad():
+        y1, y2 = blk(x), blk(x)
+    assert torch.equal(y1, y2)
+    hyb = pkg.HybridSpectralAttention(64).to(dev).eval()
+    assert hyb(x).shape == x.shape
+
+
+# ---------------------------------------------------------------------------------------------------------
+# raw C ABI (ctypes, plain pointers) -- what a non-Python host would bind
+# ---------------------------------------------------------------------------------------------------------
+def test_c_abi_direct(pkg, dev):
+    from tensor_cuda_fft_b200 import _native
+    lib = _native.lib()
+    B, T, D, F = 2, 1024, 32, 16
+    gen = torch.Generator().manual_seed(11)
+    x, g = torch.randn(B, T, D, generator=gen), torch.randn(B, T, D, generator=gen)
+    w_re, w_im, bias = torch.randn(D, F, generator=gen), torch.randn(D, F, generator=gen), torch.randn(D, generator=gen)
+    want = orc.closed_form_f64(x.numpy(), w_re.numpy(), w_im.numpy(), bias.numpy(), g.numpy())
+    d = lambda t: t.to(dev).contiguous()
+    xd, gd, wr, wi, bs = d(x), d(g), d(w_re), d(w_im), d(bias)
+    y, gx = torch.empty_like(xd), torch.empty_like(xd)
+    xlow = torch.empty(lib.sml_xlow_bytes(B, T, D, F), dtype=torch.uint8, device=dev)
+    gwr, gwi, gb = torch.full((D, F), 7.0, device=dev), torch.full((D, F), 7.0, device=dev), torch.full((D,), 7.0, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    n0 = lib.sml_launch_count()
+    assert lib.sml_forward(xd.data_ptr(), wr.data_ptr(), wi.data_ptr(), bs.data_ptr(), y.data_ptr(), xlow.data_ptr(),
+                           B, T, D, F, 0, s) == 0, lib.sml_last_error()
+    assert lib.sml_backward(gd.data_ptr(), xlow.data_ptr(), wr.data_ptr(), wi.data_ptr(), gx.data_ptr(),
+                            gwr.data_ptr(), gwi.data_ptr(), gb.data_ptr(), None, 0, B, T, D, F, 0, s) == 0, lib.sml_last_error()
+    torch.cuda.synchronize()
+    assert lib.sml_launch_count() - n0 >= 2
+    for name, a in zip(NAMES, (y, gx, gwr, gwi, gb)):      # outputs are overwritten, not accumulated
+        assert orc.rel_l2(a.cpu().numpy(), want[name]) <= TOL_F32, name
+    k = want["k"]
+    X = xlow.view(torch.complex64).view(B, D, k).cpu().numpy()
+    assert orc.rel_l2(np.transpose(X, (0, 2, 1)), want["X_low"]) <= TOL_F32
+    # errors are reported, never swallowed
+    assert lib.sml_forward(None, wr.data_ptr(), wi.data_ptr(), None, y.data_ptr(), None, B, T, D, F, 0, s) != 0
+    assert b"null" in lib.sml_last_error()
+    assert lib.sml_backward(gd.data_ptr(), None, wr.data_ptr(), wi.data_ptr(), gx.data_ptr(), gwr.data_ptr(),
+                            gwi.data_ptr(), gb.data_ptr(), None, 0, B, T, D, F, 0, s) != 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Wirtinger ops
+# ---------------------------------------------------------------------------------------------------------
+def test_wirtinger_ops_golden(pkg, dev, golden_dir):
+    z = np.load(os.path.join(golden_dir, "wirtinger.npz"))
+    t = lambda k: torch.from_numpy(z[k]).to(dev)
+    xf = t("mul_x").requires_grad_(True)
+    w = t("mul_w").requires_grad_(True)
+    out = pkg.WirtingerGradient.apply(xf, w)
+    out.backward(t("mul_g"))
+    torch.cuda.synchronize()
+    assert orc.rel_l2(out.detach().cpu().numpy(), z["mul_out"]) <= 1e-6
+    assert orc.rel_l2(xf.grad.cpu().numpy(), z["mul_gx"]) <= 1e-6
+    assert orc.rel_l2(w.grad.cpu().numpy(), z["mul_gw"]) <= 1e-6
+    D, nf = z["filt_w_re"].shape
+    filt = pkg.WirtingerSpectralFilter(D, nf)
+    with torch.no_grad():
+        filt.weight.real.copy_(torch.from_numpy(z["filt_w_re"]))
+        filt.weight.imag.copy_(torch.from_numpy(z["filt_w_im"]))
+    filt = filt.to(dev)
+    xf = t("filt_x").requires_grad_(True)
+    o = filt(xf)
+    o.backward(t("filt_g"))
+    torch.cuda.synchronize()
+    assert orc.rel_l2(o.detach().cpu().numpy(), z["filt_out"]) <= 1e-6
+    assert orc.rel_l2(xf.grad.cpu().numpy(), z["filt_gx"]) <= 1e-6
+    assert orc.rel_l2(filt.weight.real.grad.cpu().numpy(), z["filt_gw_re"]) <= 1e-6
+    assert orc.rel_l2(filt.weight.imag.grad.cpu().numpy(), z["filt_gw_im"]) <= 1e-6
+
+
+def test_wirtinger_filter_equals_fused_layer(pkg, dev):
+    # fft -> WirtingerSpectralFilter -> ifft.real == SpectralMixingLayer minus bias
+    gen = torch.Generator().manual_seed(9)
+    B, T, D = 2, 256, 64
+    layer = make_layer(pkg, D, 32, torch.randn(D, 32, generator=gen), torch.randn(D, 32, generator=gen),
+                       torch.zeros(D), dev)
+    filt = pkg.WirtingerSpectralFilter(D, 32).to(dev)
+    with torch.no_grad():
+        filt.weight.real.copy_(layer.weight_real)
+        filt.weight.imag.copy_(layer.weight_imag)
+    x = torch.randn(B, T, D, generator=gen).to(dev)
+    y1 = layer(x)
+    y2 = torch.fft.ifft(filt(torch.fft.fft(x, dim=1)), dim=1).real
+    assert orc.rel_l2(y1.detach().cpu().numpy(), y2.detach().cpu().numpy()) <= TOL_F32
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties + column spot checks against the oracle
+# ---------------------------------------------------------------------------------------------------------
+FULL = [(16, 8192, 768, torch.float32), (16, 8192, 768, torch.bfloat16), (16, 4096, 1024, torch.float32)]
+
+
+@pytest.mark.parametrize("B,T,D,dtype", FULL, ids=["cfg2_f32", "cfg2_bf16", "cfg3_b16_f32"])
+def test_full_size_properties(pkg, dev, B, T, D, dtype):
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    gen = torch.Generator(device="cpu").manual_seed(2024)
+    Fn = D // 2
+    w_re, w_im, bias = torch.randn(D, Fn, generator=gen), torch.randn(D, Fn, generator=gen), torch.randn(D, generator=gen)
+    layer = make_layer(pkg, D, Fn, w_re, w_im, bias, dev)
+    torch.manual_seed(1)
+    x = torch.randn(B, T, D, device=dev).to(dtype)
+    g = torch.randn(B, T, D, device=dev).to(dtype)
+    xg = x.clone().requires_grad_(True)
+    y = layer(xg)
+    y.backward(g)
+    torch.cuda.synchronize()
+    # (1) spot columns against the float64 closed form (columns are independent transforms)
+    for (b, d0) in [(0, 0), (B - 1, D - 16), (B // 2, 368)]:
+        sl = slice(d0, d0 + 16)
+        want = orc.closed_form_f64(x[b:b + 1, :, sl].float().cpu().numpy(), w_re[sl].numpy(), w_im[sl].numpy(),
+                                   bias[sl].numpy(), g[b:b + 1, :, sl].float().cpu().numpy())
+        assert orc.rel_l2(y[b:b + 1, :, sl].detach().float().cpu().numpy(), want["y"]) <= tol
+        assert orc.rel_l2(xg.grad[b:b + 1, :, sl].float().cpu().numpy(), want["gx"]) <= tol
+    # (2) adjoint identity <g, J x> = <J^T g, x> with J the (bias-free) linear map: ties forward and backward together
+    lhs = torch.sum(g.double() * (y.detach().double() - bias.to(dev).double())).item()
+    rhs = torch.sum(xg.grad.double() * x.double()).item()
+    assert abs(lhs - rhs) <= (5e-5 if dtype == torch.float32 else 2e-2) * max(abs(lhs), abs(rhs), 1.0)
+    # (3) bias gradient is the plain sum of g; DC column of weight_imag.grad vanishes; columns >= k are zero
+    gb_want = g.double().sum(dim=(0, 1))
+    assert orc.rel_l2(layer.bias.grad.double().cpu().numpy(), gb_want.cpu().numpy()) <= tol
+    assert layer.weight_imag.grad[:, 0].abs().max().item() <= 1e-3 * layer.weight_real.grad[:, 0].abs().max().item() + 1e-6
+    # (4) filter-gradient batch reduction: linear in the batch -> equals the sum of per-half-batch gradients
+    gw_full = layer.weight_real.grad.clone()
+    layer.zero_grad()
+    for sl in (slice(0, B // 2), slice(B // 2, B)):
+        xh = x[sl].clone().requires_grad_(True)
+        layer(xh).backward(g[sl])
+    torch.cuda.synchronize()
+    assert orc.rel_l2(layer.weight_real.grad.cpu().numpy(), gw_full.cpu().numpy()) <= 10 * tol
+    # (5) low-pass: the output has no energy above bin k (band-limited synthesis), checked on a few columns
+    Y = torch.fft.rfft(y[0, :, :8].detach().float() - bias[:8].to(dev), dim=0)
+    hi = Y[Fn:].abs().pow(2).sum().item()
+    lo = Y[:Fn].abs().pow(2).sum().item()
+    assert hi <= (1e-9 if dtype == torch.float32 else 1e-3) * lo
+
+
+def test_long_context_column(pkg, dev):
+    # BASELINE config 5 top end: T = 128K, D = 1024 geometry on a narrow slice (R = 128 passes)
+    B, T, D, Fn = 1, 131072, 32, 512
+    gen = torch.Generator().manual_seed(5)
+    w_re, w_im, bias = torch.randn(D, Fn, generator=gen), torch.randn(D, Fn, generator=gen), torch.randn(D, generator=gen)
+    x, g = torch.randn(B, T, D, generator=gen), torch.randn(B, T, D, generator=gen)
+    want = orc.closed_form_f64(x.numpy(), w_re.numpy(), w_im.numpy(), bias.numpy(), g.numpy())
+    layer = make_layer(pkg, D, Fn, w_re, w_im, bias, dev)
+    got = run_layer(layer, x, g, dev)
+    for name, a in zip(NAMES, got):
+        assert orc.rel_l2(a, want[name]) <= TOL_F32, name
