@@ -37,6 +37,10 @@ UNIT = "tokens/s"
 CFG = {"B": 16, "T": 8192, "D": 768}      # BASELINE.json configs[1]
 
 
+def _fft_backend():
+    return "MKL DFTI" if torch.backends.mkl.is_available() else "pocketfft"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -91,7 +95,7 @@ def run_reference_arm(args):
         "config": {"workload": f"SpectralMixingLayer(embed_dim={D}) fwd+bwd, x=({args.batch},{T},{D}) fp32, k={min(D // 2, T // 2)}",
                    "note": f"CPU arm: each step is a bounded sample of the workload, batch {B} of {args.batch} (columns are independent)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"oracle torch port (torch.fft, {torch.__config__.parallel_info().splitlines()[0]}), "
+                         "sample": f"oracle torch port (torch.fft, {_fft_backend()}), "
                                    f"x=({B},{T},{D}) fwd+bwd, mean of {n} steps"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -194,7 +198,7 @@ def run_ours(args):
 
     def step():
         layer.zero_grad(set_to_none=True)
-        xr = x.requires_grad_(True)
+        xr = x.detach().requires_grad_(True)
         y = layer(xr)
         y.backward(g)
         if world > 1:
@@ -292,8 +296,8 @@ def run_ours(args):
     if not args.no_e2e:
         xh = torch.empty(B, T, D, dtype=dtype).pin_memory()
         gh = torch.empty(B, T, D, dtype=dtype).pin_memory()
-        xh.copy_(x)
-        gh.copy_(g)
+        xh.copy_(x.detach())
+        gh.copy_(g.detach())
         yh = torch.empty(B, T, D, dtype=dtype).pin_memory()
         gxh = torch.empty(B, T, D, dtype=dtype).pin_memory()
         gradh = torch.empty(2 * D * Fn + D, dtype=torch.float32).pin_memory()
@@ -337,7 +341,7 @@ def run_ours(args):
         Bs = min(args.cpu_sample_batch, B)
         dt, n, threads = cpu_reference_step_time(Bs, T, D, steps=40, warmup=1, budget_s=12.0)
         cpu = {"value": Bs * T / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"oracle torch port (torch.fft on host, {torch.__config__.parallel_info().splitlines()[0]}), "
+               "sample": f"oracle torch port (torch.fft on host, {_fft_backend()}), "
                          f"x=({Bs},{T},{D}) fp32 fwd+bwd (batch {Bs} of {B}; columns independent), mean of {n} steps",
                "ms_per_step": dt * 1e3}
 

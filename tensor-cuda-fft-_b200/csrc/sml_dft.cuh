@@ -25,11 +25,130 @@ struct cf {
     float re, im;
 };
 
-SML_HD cf cmul(cf a, cf b) { return cf{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+// ------------------------------------------------------------------------------------------------
+// complex primitives.  Device code maps every one of them onto Blackwell's packed fp32x2 pipe
+// (PTX add/sub/mul/fma.rn.f32x2 -> SASS FADD2/FMUL2/FFMA2): a complex (re, im) is one 64-bit register
+// pair, and ptxas folds the half-swap (im, re), the (-,+)/(+,-) sign patterns and 32-bit scalar
+// broadcasts into operand modifiers (.LO_HI, .NP/.PN, .F32), so a complex multiply is 2 issue slots and a
+// twiddled butterfly 3 instead of 4 and 6.  Host code (unit tests) uses the scalar definitions.
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define SML_X2 1
+#else
+#define SML_X2 0
+#endif
+
+#if SML_X2
+__device__ __forceinline__ unsigned long long x2_pack(float lo, float hi) {
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ cf x2_unpack(unsigned long long v) {
+    cf r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.re), "=f"(r.im) : "l"(v));
+    return r;
+}
+// elementwise (a.re*b.re + c.re, a.im*b.im + c.im)
+__device__ __forceinline__ cf x2_fma(cf a, cf b, cf c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x2_pack(a.re, a.im)), "l"(x2_pack(b.re, b.im)), "l"(x2_pack(c.re, c.im)));
+    return x2_unpack(d);
+}
+__device__ __forceinline__ cf x2_mul(cf a, cf b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x2_pack(a.re, a.im)), "l"(x2_pack(b.re, b.im)));
+    return x2_unpack(d);
+}
+__device__ __forceinline__ cf x2_add(cf a, cf b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x2_pack(a.re, a.im)), "l"(x2_pack(b.re, b.im)));
+    return x2_unpack(d);
+}
+__device__ __forceinline__ cf x2_sub(cf a, cf b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x2_pack(a.re, a.im)), "l"(x2_pack(b.re, b.im)));
+    return x2_unpack(d);
+}
+#endif
+
+SML_HD cf cadd(cf a, cf b) {
+#if SML_X2
+    return x2_add(a, b);
+#else
+    return cf{a.re + b.re, a.im + b.im};
+#endif
+}
+SML_HD cf csub(cf a, cf b) {
+#if SML_X2
+    return x2_sub(a, b);
+#else
+    return cf{a.re - b.re, a.im - b.im};
+#endif
+}
+// e + s*u  (real scalar s)
+SML_HD cf caxpy(float s, cf u, cf e) {
+#if SML_X2
+    return x2_fma(u, cf{s, s}, e);
+#else
+    return cf{s * u.re + e.re, s * u.im + e.im};
+#endif
+}
+// o * (1 + i*t) = (o.re - t*o.im, o.im + t*o.re)
+SML_HD cf crot(cf o, float t) {
+#if SML_X2
+    return x2_fma(cf{o.im, o.re}, cf{-t, t}, o);
+#else
+    return cf{o.re - t * o.im, o.im + t * o.re};
+#endif
+}
+// a + i*b  and  a - i*b
+SML_HD cf cadd_i(cf a, cf b) {
+#if SML_X2
+    return x2_add(a, cf{-b.im, b.re});
+#else
+    return cf{a.re - b.im, a.im + b.re};
+#endif
+}
+SML_HD cf csub_i(cf a, cf b) {
+#if SML_X2
+    return x2_add(a, cf{b.im, -b.re});
+#else
+    return cf{a.re + b.im, a.im - b.re};
+#endif
+}
+// a * b
+SML_HD cf cmul(cf a, cf b) {
+#if SML_X2
+    return x2_fma(cf{a.im, a.re}, cf{-b.im, b.im}, x2_mul(a, cf{b.re, b.re}));
+#else
+    return cf{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+#endif
+}
 // a * conj(b)
-SML_HD cf cmulc(cf a, cf b) { return cf{a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im}; }
-SML_HD cf cadd(cf a, cf b) { return cf{a.re + b.re, a.im + b.im}; }
-SML_HD cf csub(cf a, cf b) { return cf{a.re - b.re, a.im - b.im}; }
+SML_HD cf cmulc(cf a, cf b) {
+#if SML_X2
+    return x2_fma(cf{a.im, a.re}, cf{b.im, -b.im}, x2_mul(a, cf{b.re, b.re}));
+#else
+    return cf{a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im};
+#endif
+}
+// acc + a * b
+SML_HD cf cmac(cf acc, cf a, cf b) {
+#if SML_X2
+    return x2_fma(cf{a.im, a.re}, cf{-b.im, b.im}, x2_fma(a, cf{b.re, b.re}, acc));
+#else
+    return cf{acc.re + a.re * b.re - a.im * b.im, acc.im + a.re * b.im + a.im * b.re};
+#endif
+}
+// s * a  (real scalar)
+SML_HD cf cscale(float s, cf a) {
+#if SML_X2
+    return x2_mul(a, cf{s, s});
+#else
+    return cf{s * a.re, s * a.im};
+#endif
+}
 
 #if defined(__CUDA_ARCH__)
 #define SML_FMA(a, b, c) __fmaf_rn((a), (b), (c))
@@ -80,19 +199,21 @@ SML_HD void butterfly(const cf e, const cf o, cf& lo, cf& hi) {
         lo = cadd(e, o);
         hi = csub(e, o);
     } else if constexpr (4 * K == N) {
-        // w = DIR * i : w*o = DIR * (-o.im, o.re)
-        const cf t = (DIR < 0) ? cf{o.im, -o.re} : cf{-o.im, o.re};
-        lo = cadd(e, t);
-        hi = csub(e, t);
+        // w = DIR * i
+        if constexpr (DIR < 0) {
+            lo = csub_i(e, o);
+            hi = cadd_i(e, o);
+        } else {
+            lo = cadd_i(e, o);
+            hi = csub_i(e, o);
+        }
     } else {
+        // w = c (1 + i t):  lo/hi = e +- c * (o (1 + i t))      -- 3 packed FMAs
         constexpr float c = Tw<N, K, DIR>::c;
         constexpr float t = Tw<N, K, DIR>::t;
-        const float ur = SML_FMA(-t, o.im, o.re);
-        const float ui = SML_FMA(t, o.re, o.im);
-        lo.re = SML_FMA(c, ur, e.re);
-        lo.im = SML_FMA(c, ui, e.im);
-        hi.re = SML_FMA(-c, ur, e.re);
-        hi.im = SML_FMA(-c, ui, e.im);
+        const cf u = crot(o, t);
+        lo = caxpy(c, u, e);
+        hi = caxpy(-c, u, e);
     }
 }
 

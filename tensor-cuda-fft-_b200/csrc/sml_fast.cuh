@@ -265,9 +265,7 @@ __global__ void __launch_bounds__(NR* P, 1)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     const int f2 = j < KJ ? j : NR - NJ + j;
-                    const cf c = cjs[f2];
-                    acc[j].re = SML_FMA(v[f2].re, c.re, SML_FMA(-v[f2].im, c.im, acc[j].re));
-                    acc[j].im = SML_FMA(v[f2].re, c.im, SML_FMA(v[f2].im, c.re, acc[j].im));
+                    acc[j] = cmac(acc[j], v[f2], cjs[f2]);
                 }
             }
             slot ^= 1;
@@ -388,11 +386,13 @@ __global__ void __launch_bounds__(NR* P, 1)
             }
             Dft<NR, +1>::run(v);   // over f1 -> m1
             if (td0 < D) {
-                IO* dst = outp + ((size_t)b * T + r + (size_t)R * tm2) * D + td0;
-                const size_t step = (size_t)R * NR * D;
+                // row of m1 is r + R*(NR*m1 + m2): one 32x32->64 multiply-add per store address
+                char* dst = reinterpret_cast<char*>(outp + ((size_t)b * T + r + (size_t)R * tm2) * D + td0);
+                const uint32_t step = (uint32_t)R * NR * (uint32_t)D * (uint32_t)sizeof(IO);
+                const cf bias2 = cf{bias0, bias1};
 #pragma unroll
                 for (int m1 = 0; m1 < NR; ++m1)
-                    PairIO<IO>::store_g(dst + m1 * step, cf{v[m1].re + bias0, v[m1].im + bias1});
+                    PairIO<IO>::store_g(reinterpret_cast<IO*>(dst + (uint64_t)step * (uint32_t)m1), cadd(v[m1], bias2));
             }
             slot ^= 1;
         }
