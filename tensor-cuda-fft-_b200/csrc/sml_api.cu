@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -87,6 +88,7 @@ struct Plan {
     int path = SML_PATH_GENERIC;
     int k = 0;
     int NR = 0, KJ = 0, P = 0, M = 0, R = 0;
+    int ctas_per_sm = 1;
 };
 
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -99,7 +101,7 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
     if ((D * esz) % 16 != 0) return p;   // TMA global strides must be multiples of 16 bytes (and D even)
     // smallest supported square sub-transform M = NR*NR >= 2k that still fits into T
     static const int kNR[3] = {8, 16, 32};
-    static const int kP[3] = {32, 16, 8};
+    static const int kP[3] = {32, 8, 4};   // channel pairs per CTA
     for (int i = 0; i < 3; ++i) {
         const int M = kNR[i] * kNR[i];
         if (M >= 2 * p.k && M <= T) {
@@ -108,11 +110,17 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
             p.P = kP[i];
             p.M = M;
             p.R = T / M;
+            p.ctas_per_sm = p.NR == 8 ? 2 : 3;   // CTAs per SM the kernel variant is compiled for (register budget)
+            // TMA store address arithmetic and box coordinates stay in 32 bits
             const int need = (p.k + p.NR - 1) / p.NR;   // positive f2 columns that hold live bins
             // instantiated KJ values per NR (see launch_fast)
             if (p.NR == 32) p.KJ = need <= 8 ? 8 : need <= 12 ? 12 : 16;
             else if (p.NR == 16) p.KJ = need <= 4 ? 4 : 8;
             else p.KJ = 4;
+            if (p.NR == 32 && p.KJ == 16) p.ctas_per_sm = 2;   // 64 accumulator registers: 3 CTAs/SM would spill
+            if (const char* e = getenv("SML_FAST_CTAS")) {   // tuning knob for the NR=32, KJ=12 kernel: 2 or 3 CTAs per SM
+                if (atoi(e) == 2 && p.NR == 32 && p.KJ == 12) p.ctas_per_sm = 2;
+            }
             return p;
         }
     }
@@ -142,7 +150,7 @@ int get_encode_fn(EncodeTiledFn* out) {
 }
 
 // view of a (B, T, D) activation as the 4-D tensor {D, R, M, B}: t = R*m + r
-int encode_input_map(CUtensorMap* map, const void* base, int B, int T, int D, int io_dtype, const Plan& p) {
+int encode_act_map(CUtensorMap* map, const void* base, int B, int T, int D, int io_dtype, const Plan& p) {
     EncodeTiledFn enc;
     if (get_encode_fn(&enc)) return 1;
     const cuuint64_t esz = io_dtype == SML_DTYPE_BF16 ? 2 : 4;
@@ -161,34 +169,37 @@ int encode_input_map(CUtensorMap* map, const void* base, int B, int T, int D, in
 // ------------------------------------------------------------------------------------------------
 // fast-path launch
 // ------------------------------------------------------------------------------------------------
-template <int NR, int KJ, int P, typename IO, bool BWD>
-int launch_fast_inst(const CUtensorMap& map, const sml::FastParams& prm, int grid, cudaStream_t stream) {
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD>
+int launch_fast_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
+                     cudaStream_t stream) {
     using C = sml::FastCfg<NR, P, IO>;
-    auto kern = sml::sml_fast_kernel<NR, KJ, P, IO, BWD>;
+    auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD>;
     static std::once_flag once;   // one per instantiation
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] {
         attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
     });
     if (attr_err != cudaSuccess) return fail("cudaFuncSetAttribute(smem=%zu) failed: %s", C::SMEM_BYTES, cudaGetErrorString(attr_err));
-    kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map, prm);
+    kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map_in, map_out, prm);
     count_launch();
     SML_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <typename IO, bool BWD>
-int launch_fast(const Plan& p, const CUtensorMap& map, const sml::FastParams& prm, int grid, cudaStream_t stream) {
-#define SML_CASE(NR_, KJ_, P_) \
-    if (p.NR == NR_ && p.KJ == KJ_) return launch_fast_inst<NR_, KJ_, P_, IO, BWD>(map, prm, grid, stream);
-    SML_CASE(32, 8, 8)
-    SML_CASE(32, 12, 8)
-    SML_CASE(32, 16, 8)
-    SML_CASE(16, 4, 16)
-    SML_CASE(16, 8, 16)
-    SML_CASE(8, 4, 32)
+int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm,
+                int grid, cudaStream_t stream) {
+#define SML_CASE(NR_, KJ_, P_, MINB_) \
+    if (p.NR == NR_ && p.KJ == KJ_ && p.P == P_ && p.ctas_per_sm == MINB_) return launch_fast_inst<NR_, KJ_, P_, MINB_, IO, BWD>(map_in, map_out, prm, grid, stream);
+    SML_CASE(32, 8, 4, 3)
+    SML_CASE(32, 12, 4, 3)
+    SML_CASE(32, 16, 4, 2)
+    SML_CASE(32, 12, 4, 2)
+    SML_CASE(16, 4, 8, 3)
+    SML_CASE(16, 8, 8, 3)
+    SML_CASE(8, 4, 32, 2)
 #undef SML_CASE
-    return fail("internal: no fast kernel for NR=%d KJ=%d", p.NR, p.KJ);
+    return fail("internal: no fast kernel for NR=%d KJ=%d P=%d", p.NR, p.KJ, p.P);
 }
 
 int check_common(const void* a, const void* b, int B, int T, int D, int F, int io_dtype) {
@@ -209,10 +220,11 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
     const sml::cf* gtab = nullptr;
     if (twiddle_table(st, T, stream, &gtab)) return 1;
     const float invT = 1.0f / (float)T;
-    const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 8 == 0);
+    const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
     if (p.path == SML_PATH_FAST && aligned) {
-        CUtensorMap map;
-        if (encode_input_map(&map, x, B, T, D, io_dtype, p)) return 1;
+        CUtensorMap map, map_out;
+        if (encode_act_map(&map, x, B, T, D, io_dtype, p)) return 1;
+        if (encode_act_map(&map_out, y, B, T, D, io_dtype, p)) return 1;
         sml::FastParams prm{};
         prm.out = y; prm.w_re = w_re; prm.w_im = w_im; prm.bias = bias;
         prm.xlow = reinterpret_cast<sml::cf*>(xlow);
@@ -221,8 +233,9 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
         prm.ntd = (D + 2 * p.P - 1) / (2 * p.P);
         prm.ntiles = B * prm.ntd;
         prm.invT = invT;
-        const int grid = prm.ntiles < st->sm_count ? prm.ntiles : st->sm_count;
-        return launch_fast<IO, false>(p, map, prm, grid, stream);
+        const int slots = st->sm_count * p.ctas_per_sm;
+        const int grid = prm.ntiles < slots ? prm.ntiles : slots;
+        return launch_fast<IO, false>(p, map, map_out, prm, grid, stream);
     }
     // generic path
     if (p.k > 0 && xlow == nullptr) return fail("generic path needs the xlow buffer (sml_xlow_bytes) as scratch");
@@ -254,15 +267,16 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
     const sml::cf* gtab = nullptr;
     if (twiddle_table(st, T, stream, &gtab)) return 1;
     const float invT = 1.0f / (float)T;
-    const bool aligned = ((uintptr_t)g % 16 == 0) && ((uintptr_t)gx % 8 == 0);
+    const bool aligned = ((uintptr_t)g % 16 == 0) && ((uintptr_t)gx % 16 == 0);
     if (p.path == SML_PATH_FAST && aligned) {
         if (want_grads) {
             SML_CUDA(cudaMemsetAsync(gw_re, 0, sizeof(float) * (size_t)D * F, stream));
             SML_CUDA(cudaMemsetAsync(gw_im, 0, sizeof(float) * (size_t)D * F, stream));
             SML_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)D, stream));
         }
-        CUtensorMap map;
-        if (encode_input_map(&map, g, B, T, D, io_dtype, p)) return 1;
+        CUtensorMap map, map_out;
+        if (encode_act_map(&map, g, B, T, D, io_dtype, p)) return 1;
+        if (encode_act_map(&map_out, gx, B, T, D, io_dtype, p)) return 1;
         sml::FastParams prm{};
         prm.out = gx; prm.w_re = w_re; prm.w_im = w_im; prm.bias = nullptr;
         prm.xlow = reinterpret_cast<sml::cf*>(const_cast<void*>(xlow));
@@ -272,8 +286,9 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         prm.ntd = (D + 2 * p.P - 1) / (2 * p.P);
         prm.ntiles = B * prm.ntd;
         prm.invT = invT;
-        const int grid = prm.ntiles < st->sm_count ? prm.ntiles : st->sm_count;
-        return launch_fast<IO, true>(p, map, prm, grid, stream);
+        const int slots = st->sm_count * p.ctas_per_sm;
+        const int grid = prm.ntiles < slots ? prm.ntiles : slots;
+        return launch_fast<IO, true>(p, map, map_out, prm, grid, stream);
     }
     // generic path: G into workspace, then synthesis with conj(W) and the batch reduction
     const size_t need = sizeof(sml::cf) * (size_t)B * D * (size_t)p.k;

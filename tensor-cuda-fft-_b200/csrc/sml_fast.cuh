@@ -18,8 +18,14 @@
 // Thread mappings (NT = NR*P threads, P channel pairs per CTA):
 //   time side  : tid -> (p = tid % P, m2 = tid / P)   rows m = NR*m1 + m2 ; coalesced 8*P-byte row segments
 //   freq side  : tid -> (f1 = tid % NR, p = tid / NR) bins f = f1 + NR*f2 ; partner bin -f is in the same warp
-// Global -> shared staging is TMA (cp.async.bulk.tensor.4d) double buffered over passes and tiles; the
-// kernel is persistent (one CTA per SM, static round-robin over (batch, channel-tile) work items).
+// Global <-> shared traffic is all TMA (cp.async.bulk.tensor.4d loads with mbarrier completion, bulk-group
+// stores).  Each CTA owns two shared buffers: X = TMA landing zone (analysis) / output staging (synthesis),
+// Y = padded exchange buffer.  The load of pass r+1 is issued as soon as every thread has pulled pass r out of X,
+// the store of pass r-1 drains while pass r is computed.  Inter-stage twiddles W_T^{(R m2 + r) f1} are powers of
+// one per-thread base and are generated in registers (no table traffic through shared memory).
+// The kernel is persistent (static round-robin over (batch, channel-tile) work items); with P = 4 pairs a CTA
+// is 4 warps and three CTAs share an SM and drift out of phase, which is what keeps the FMA, shared-memory
+// and TMA pipes busy at the same time.
 #pragma once
 
 #include <cuda.h>
@@ -93,6 +99,20 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tmap, 
         : "memory");
 }
 
+// 4-D tiled TMA store shared -> global (bulk async group; SASS: UTMASTG).  Out-of-range elements are clipped.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk stores issued by this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // element I/O: one channel pair (d, d+1) <-> complex
 // ------------------------------------------------------------------------------------------------
@@ -104,7 +124,7 @@ struct PairIO<float> {
         const float2 v = *reinterpret_cast<const float2*>(p);
         return cf{v.x, v.y};
     }
-    static __device__ __forceinline__ void store_g(float* p, cf v) {
+    static __device__ __forceinline__ void store_s(float* p, cf v) {
         *reinterpret_cast<float2*>(p) = make_float2(v.re, v.im);
     }
 };
@@ -114,7 +134,7 @@ struct PairIO<__nv_bfloat16> {
         const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
         return cf{v.x, v.y};
     }
-    static __device__ __forceinline__ void store_g(__nv_bfloat16* p, cf v) {
+    static __device__ __forceinline__ void store_s(__nv_bfloat16* p, cf v) {
         *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.re, v.im);
     }
 };
@@ -123,102 +143,106 @@ template <int NR, int P, typename IO>
 struct FastCfg {
     static constexpr int NT = NR * P;
     static constexpr int M = NR * NR;
-    static constexpr int XS = NR + 1;    // exchange row stride (complex): odd -> conflict-free both ways
-    static constexpr int TS = NR + 2;    // twiddle row stride (complex): 16-byte aligned rows, 4-bank skew
-    static constexpr int NBUF = 2;       // TMA stages
+    static constexpr int XS = NR + 2;    // exchange row stride (complex): rows stay 16-byte aligned (128-bit row access)
     static constexpr int BOXROWS = M < 256 ? M : 256;
     static constexpr int NBOX = M / BOXROWS;
-    static constexpr uint32_t STAGE_BYTES = (uint32_t)M * 2u * P * sizeof(IO);
-    static constexpr size_t SMEM_BYTES = (size_t)NBUF * STAGE_BYTES + (size_t)NT * XS * sizeof(cf) +
-                                         2u * NR * TS * sizeof(cf) + 2u * NR * sizeof(cf) + NBUF * sizeof(uint64_t);
-    static constexpr int TWPT = (M + NT - 1) / NT;   // twiddle-table entries each thread rebuilds per pass
+    static constexpr uint32_t LOAD_BYTES = (uint32_t)M * 2u * P * sizeof(IO);            // X: one TMA stage, dense [M][2P]
+    static constexpr uint32_t XBUF_BYTES = (LOAD_BYTES + 127u) & ~127u;
+    static constexpr uint32_t YBUF_BYTES = ((uint32_t)NT * XS * sizeof(cf) + 127u) & ~127u;   // Y: exchange [NT][XS]
+    static constexpr size_t SMEM_BYTES = (size_t)XBUF_BYTES + YBUF_BYTES + 2u * NR * sizeof(cf) + 2 * sizeof(uint64_t);
 };
+
+// v[i] *= (or *= conj of) base0 * step^i for i in [0, NR): twiddle powers generated in registers, 8 at a time.
+// q holds base0*step^{8h+lo}; step8 = step^8.  CONJ multiplies by the conjugate instead.
+template <int NR, bool CONJ, bool UNIT_BASE>
+__device__ __forceinline__ void apply_power_twiddles(cf (&v)[NR], const cf base0, const cf step) {
+    static_assert(NR % 8 == 0, "NR must be a multiple of 8");
+    const cf s2 = cmul(step, step);
+    const cf s4 = cmul(s2, s2);
+    const cf s8 = cmul(s4, s4);
+    cf q[8];
+    q[0] = base0;
+    q[1] = UNIT_BASE ? step : cmul(base0, step);
+    q[2] = UNIT_BASE ? s2 : cmul(base0, s2);
+    q[3] = cmul(q[1], s2);
+    q[4] = UNIT_BASE ? s4 : cmul(base0, s4);
+    q[5] = cmul(q[1], s4);
+    q[6] = cmul(q[2], s4);
+    q[7] = cmul(q[3], s4);
+#pragma unroll
+    for (int h = 0; h < NR / 8; ++h) {
+#pragma unroll
+        for (int lo = 0; lo < 8; ++lo) {
+            if (UNIT_BASE && h == 0 && lo == 0) continue;   // multiply by 1
+            v[8 * h + lo] = CONJ ? cmulc(v[8 * h + lo], q[lo]) : cmul(v[8 * h + lo], q[lo]);
+        }
+        if (h + 1 < NR / 8) {
+#pragma unroll
+            for (int lo = 0; lo < 8; ++lo) q[lo] = (UNIT_BASE && h == 0 && lo == 0) ? s8 : cmul(q[lo], s8);
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int NR, int KJ, int P, typename IO, bool BWD>
-__global__ void __launch_bounds__(NR* P, 1)
-    sml_fast_kernel(const __grid_constant__ CUtensorMap tmap, const FastParams prm) {
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD>
+__global__ void __launch_bounds__(NR* P, MINB)
+    sml_fast_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
+                    const FastParams prm) {
     using C = FastCfg<NR, P, IO>;
-    constexpr int NT = C::NT, M = C::M, XS = C::XS, TS = C::TS, NBUF = C::NBUF;
+    constexpr int NT = C::NT, M = C::M, XS = C::XS;
     constexpr int NJ = 2 * KJ;   // live f2 columns held per thread: [0,KJ) and [NR-KJ, NR)
     static_assert(NJ <= NR, "band wider than the sub-transform");
     static_assert(NT % 32 == 0 && 32 % NR == 0, "freq-side partner bin must live in the same warp");
 
     extern __shared__ __align__(1024) unsigned char smem[];
-    IO* tbuf = reinterpret_cast<IO*>(smem);                                  // [NBUF][M][2P]
-    cf* xch = reinterpret_cast<cf*>(smem + (size_t)NBUF * C::STAGE_BYTES);   // [NT][XS]
-    cf* tw = xch + NT * XS;                                                  // [2][NR][TS]   W_T^{(R m2 + r) f1}
-    cf* cj = tw + 2 * NR * TS;                                               // [2][NR]       W_T^{NR r f2s}
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(cj + 2 * NR);               // [NBUF]
+    unsigned char* const xbuf = smem;                                                    // landing / staging
+    cf* const ybuf = reinterpret_cast<cf*>(smem + C::XBUF_BYTES);                        // exchange [NT][XS]
+    cf* const cj = reinterpret_cast<cf*>(smem + C::XBUF_BYTES + C::YBUF_BYTES);          // [2][NR]  W_T^{NR r f2s}
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(cj + 2 * NR);                     // [1]
 
     const int tid = threadIdx.x;
     const int tp = tid % P, tm2 = tid / P;      // time-side mapping
     const int ff1 = tid % NR, fp2 = tid / NR;   // freq-side mapping
     const int R = prm.R, T = prm.T, D = prm.D;
+    const float2* const gtab = reinterpret_cast<const float2*>(prm.gtab);
 
     const int my_ntiles = (prm.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_loads = my_ntiles * R;
 
-    auto issue_load = [&](int L) {   // thread 0 only
+    auto issue_load = [&](int L) {   // thread 0 only.  load L = (tile L / R, pass L % R) -> X
         if (L >= total_loads) return;
         const int it = L / R, r = L - it * R;
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         const int b = tile / prm.ntd, dt = tile - b * prm.ntd;
-        const int s = L % NBUF;
-        mbar_expect_tx(&mbar[s], C::STAGE_BYTES);
+        fence_proxy_async();
+        mbar_expect_tx(mbar, C::LOAD_BYTES);
 #pragma unroll
         for (int bx = 0; bx < C::NBOX; ++bx)
-            tma_load_4d(tbuf + (size_t)s * M * 2 * P + (size_t)bx * C::BOXROWS * 2 * P, &tmap, &mbar[s], dt * 2 * P, r,
-                        bx * C::BOXROWS, b);
+            tma_load_4d(xbuf + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), &tmap_in, mbar, dt * 2 * P, r, bx * C::BOXROWS, b);
     };
-
-    // twiddle tables for the NEXT pass are fetched from the global W_T table early and parked in registers
-    cf twpre[C::TWPT];
-    cf cjpre = cf{1.f, 0.f};
-    auto tw_fetch = [&](int rn) {
+    auto issue_store = [&](int b, int dt, int r) {   // thread 0 only: X -> rows r + R*m of the output
 #pragma unroll
-        for (int i = 0; i < C::TWPT; ++i) {
-            const int idx = tid + i * NT;
-            if (idx < M) {
-                const int m2 = idx / NR, f1 = idx % NR;
-                const float2 w = __ldg(reinterpret_cast<const float2*>(prm.gtab) + (R * m2 + rn) * f1);
-                twpre[i] = cf{w.x, w.y};
-            }
-        }
-        if (tid < NR) {
-            const int f2s = tid < NR / 2 ? tid : tid - NR;
-            const float2 w = __ldg(reinterpret_cast<const float2*>(prm.gtab) + ((NR * rn * f2s) & (T - 1)));
-            cjpre = cf{w.x, w.y};
-        }
+        for (int bx = 0; bx < C::NBOX; ++bx)
+            tma_store_4d(&tmap_out, xbuf + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), dt * 2 * P, r, bx * C::BOXROWS, b);
+        tma_store_commit();
     };
-    auto tw_store = [&](int slot) {
-#pragma unroll
-        for (int i = 0; i < C::TWPT; ++i) {
-            const int idx = tid + i * NT;
-            if (idx < M) tw[slot * NR * TS + (idx / NR) * TS + (idx % NR)] = twpre[i];
-        }
-        if (tid < NR) cj[slot * NR + tid] = cjpre;
+    // uniform twiddle of pass r for column f2 = tid (threads < NR): W_T^{NR r f2s}
+    auto cj_load = [&](int r) -> float2 {
+        const int f2s = tid < NR / 2 ? tid : tid - NR;
+        return __ldg(gtab + ((NR * r * f2s) & (T - 1)));
     };
 
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NBUF; ++s) mbar_init(&mbar[s], 1);
+        mbar_init(mbar, 1);
         fence_mbar_init();
     }
     __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NBUF; ++s) issue_load(s);
-    }
-    tw_fetch(0);
-    tw_store(0);
-    __syncthreads();
+    if (tid == 0) issue_load(0);
 
     int L = 0;      // loads consumed so far
-    int slot = 0;   // twiddle slot of the current pass
-    IO* const outp = reinterpret_cast<IO*>(prm.out);
+    int slot = 0;   // cj slot of the current pass
 
     for (int it = 0; it < my_ntiles; ++it) {
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -230,35 +254,39 @@ __global__ void __launch_bounds__(NR* P, 1)
 
         // ===================== analysis: R streamed passes, band accumulated in registers =====================
         for (int r = 0; r < R; ++r) {
-            tw_fetch(r + 1 == R ? 0 : r + 1);
-            mbar_wait(&mbar[L % NBUF], (uint32_t)(L / NBUF) & 1u);
+            // twiddle seeds for this pass (consumed after the first DFT / after barrier (A))
+            const float2 wb = __ldg(gtab + (R * tm2 + r));   // W_T^{R m2 + r}
+            float2 cjv = make_float2(1.f, 0.f), cjn = make_float2(1.f, 0.f);
+            if (tid < NR) {
+                cjv = cj_load(r);
+                if (r + 1 == R) cjn = cj_load(0);   // first synthesis pass
+            }
+            mbar_wait(mbar, (uint32_t)L & 1u);
             cf v[NR];
             {
-                const IO* src = tbuf + (size_t)(L % NBUF) * M * 2 * P + tm2 * 2 * P + 2 * tp;
+                const IO* src = reinterpret_cast<const IO*>(xbuf) + tm2 * 2 * P + 2 * tp;
 #pragma unroll
                 for (int m1 = 0; m1 < NR; ++m1) v[m1] = PairIO<IO>::load_s(src + m1 * NR * 2 * P);
             }
             Dft<NR, -1>::run(v);   // over m1 -> f1
+            apply_power_twiddles<NR, false, true>(v, cf{1.f, 0.f}, cf{wb.x, wb.y});   // v[f1] *= W_T^{(R m2 + r) f1}
+            __syncthreads();   // (A) everyone has pulled the landed tile out of X; last pass's exchange reads are done
+            if (tid == 0 && r + 1 < R) issue_load(L + 1);   // X becomes the staging buffer after the last pass
             {
-                const float4* twr = reinterpret_cast<const float4*>(tw + slot * NR * TS + tm2 * TS);
+                float4* xrow = reinterpret_cast<float4*>(ybuf + tid * XS);
 #pragma unroll
-                for (int h = 0; h < NR / 2; ++h) {
-                    const float4 q = twr[h];
-                    if (h > 0) v[2 * h] = cmul(v[2 * h], cf{q.x, q.y});
-                    v[2 * h + 1] = cmul(v[2 * h + 1], cf{q.z, q.w});
-                }
+                for (int h = 0; h < NR / 2; ++h) xrow[h] = make_float4(v[2 * h].re, v[2 * h].im, v[2 * h + 1].re, v[2 * h + 1].im);
             }
-            __syncthreads();   // (A) everyone is done with tbuf[L%NBUF], tw[slot] and last pass's xch reads
-            {
-                cf* xrow = xch + tid * XS;
-#pragma unroll
-                for (int f1 = 0; f1 < NR; ++f1) xrow[f1] = v[f1];
+            if (tid < NR) {
+                cj[slot * NR + tid] = cf{cjv.x, cjv.y};
+                if (r + 1 == R) cj[(slot ^ 1) * NR + tid] = cf{cjn.x, cjn.y};
             }
-            if (tid == 0) issue_load(L + NBUF);
-            tw_store(slot ^ 1);
             __syncthreads();   // (B)
+            {
+                const cf* xb = ybuf + fp2 * XS + ff1;
 #pragma unroll
-            for (int m2 = 0; m2 < NR; ++m2) v[m2] = xch[(m2 * P + fp2) * XS + ff1];
+                for (int m2 = 0; m2 < NR; ++m2) v[m2] = xb[m2 * P * XS];
+            }
             Dft<NR, -1>::run(v);   // over m2 -> f2   (outputs outside the band are dead code)
             {
                 const cf* cjs = cj + slot * NR;
@@ -346,17 +374,18 @@ __global__ void __launch_bounds__(NR* P, 1)
             }
         }
 
-        // ===================== synthesis: transpose of analysis, each output row written once =====================
+        // ===================== synthesis: transpose of analysis; rows leave through a TMA store from X =====================
         const int td0 = dt * 2 * P + 2 * tp;   // time-side channel pair
-        float bias0 = 0.f, bias1 = 0.f;
+        cf bias2 = cf{0.f, 0.f};
         if constexpr (!BWD) {
-            if (prm.bias != nullptr && td0 < D) {
-                bias0 = __ldg(prm.bias + td0);
-                bias1 = __ldg(prm.bias + td0 + 1);
-            }
+            if (prm.bias != nullptr && td0 < D) bias2 = cf{__ldg(prm.bias + td0), __ldg(prm.bias + td0 + 1)};
         }
         for (int r = 0; r < R; ++r) {
-            tw_fetch(r + 1 == R ? 0 : r + 1);
+            // twiddle seeds: v[m2] *= conj(W_T^{r f1} * (W_T^{R f1})^{m2})
+            const float2 sr = __ldg(gtab + r * ff1);
+            const float2 beta = __ldg(gtab + R * ff1);
+            float2 cjn = make_float2(1.f, 0.f);
+            if (tid < NR && r + 1 < R) cjn = cj_load(r + 1);
             cf v[NR];
             {
                 const cf* cjs = cj + slot * NR;
@@ -369,34 +398,43 @@ __global__ void __launch_bounds__(NR* P, 1)
                 }
             }
             Dft<NR, +1>::run(v);   // over f2 -> m2
+            apply_power_twiddles<NR, true, false>(v, cf{sr.x, sr.y}, cf{beta.x, beta.y});
+            __syncthreads();   // (A') previous exchange readers are done; previous pass's staging rows are complete
+            if (tid == 0 && r > 0) issue_store(b, dt, r - 1);
             {
-                const cf* twc = tw + slot * NR * TS + ff1;
+                cf* xb = ybuf + fp2 * XS + ff1;
 #pragma unroll
-                for (int m2 = 0; m2 < NR; ++m2) v[m2] = cmulc(v[m2], twc[m2 * TS]);
+                for (int m2 = 0; m2 < NR; ++m2) xb[m2 * P * XS] = v[m2];
             }
-            __syncthreads();   // (A') previous xch readers are done
-#pragma unroll
-            for (int m2 = 0; m2 < NR; ++m2) xch[(m2 * P + fp2) * XS + ff1] = v[m2];
-            tw_store(slot ^ 1);
+            if (tid < NR && r + 1 < R) cj[(slot ^ 1) * NR + tid] = cf{cjn.x, cjn.y};
+            if (tid == 0 && r > 0) tma_store_wait_read();   // X may be overwritten after (B')
             __syncthreads();   // (B')
             {
-                const cf* xrow = xch + tid * XS;
+                const float4* xrow = reinterpret_cast<const float4*>(ybuf + tid * XS);
 #pragma unroll
-                for (int f1 = 0; f1 < NR; ++f1) v[f1] = xrow[f1];
+                for (int h = 0; h < NR / 2; ++h) {
+                    const float4 q = xrow[h];
+                    v[2 * h] = cf{q.x, q.y};
+                    v[2 * h + 1] = cf{q.z, q.w};
+                }
             }
             Dft<NR, +1>::run(v);   // over f1 -> m1
-            if (td0 < D) {
-                // row of m1 is r + R*(NR*m1 + m2): one 32x32->64 multiply-add per store address
-                char* dst = reinterpret_cast<char*>(outp + ((size_t)b * T + r + (size_t)R * tm2) * D + td0);
-                const uint32_t step = (uint32_t)R * NR * (uint32_t)D * (uint32_t)sizeof(IO);
-                const cf bias2 = cf{bias0, bias1};
+            {
+                IO* dst = reinterpret_cast<IO*>(xbuf) + tm2 * 2 * P + 2 * tp;
 #pragma unroll
-                for (int m1 = 0; m1 < NR; ++m1)
-                    PairIO<IO>::store_g(reinterpret_cast<IO*>(dst + (uint64_t)step * (uint32_t)m1), cadd(v[m1], bias2));
+                for (int m1 = 0; m1 < NR; ++m1) PairIO<IO>::store_s(dst + m1 * NR * 2 * P, cadd(v[m1], bias2));
             }
+            fence_proxy_async();
             slot ^= 1;
         }
+        __syncthreads();   // (C') last staging tile complete
+        if (tid == 0) {
+            issue_store(b, dt, R - 1);
+            tma_store_wait_read();
+            issue_load(L);   // pass 0 of the next tile
+        }
     }
+    if (tid == 0) tma_store_wait_all();
 }
 
 }   // namespace sml
