@@ -121,6 +121,9 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
             if (const char* e = getenv("SML_FAST_CTAS")) {   // tuning knob for the NR=32, KJ=12 kernel: 2 or 3 CTAs per SM
                 if (atoi(e) == 2 && p.NR == 32 && p.KJ == 12) p.ctas_per_sm = 2;
             }
+            if (const char* e = getenv("SML_FAST_P")) {      // tuning knob: 6 pairs per CTA (48-byte TMA rows), 2 CTAs per SM
+                if (atoi(e) == 6 && p.NR == 32 && p.KJ == 12) { p.P = 6; p.ctas_per_sm = 2; }
+            }
             return p;
         }
     }
@@ -195,6 +198,7 @@ int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map
     SML_CASE(32, 12, 4, 3)
     SML_CASE(32, 16, 4, 2)
     SML_CASE(32, 12, 4, 2)
+    SML_CASE(32, 12, 6, 2)
     SML_CASE(16, 4, 8, 3)
     SML_CASE(16, 8, 8, 3)
     SML_CASE(8, 4, 32, 2)

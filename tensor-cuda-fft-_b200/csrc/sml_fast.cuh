@@ -149,7 +149,7 @@ struct FastCfg {
     static constexpr uint32_t LOAD_BYTES = (uint32_t)M * 2u * P * sizeof(IO);            // X: one TMA stage, dense [M][2P]
     static constexpr uint32_t XBUF_BYTES = (LOAD_BYTES + 127u) & ~127u;
     static constexpr uint32_t YBUF_BYTES = ((uint32_t)NT * XS * sizeof(cf) + 127u) & ~127u;   // Y: exchange [NT][XS]
-    static constexpr size_t SMEM_BYTES = (size_t)XBUF_BYTES + YBUF_BYTES + 2u * NR * sizeof(cf) + 2 * sizeof(uint64_t);
+    static constexpr size_t SMEM_BYTES = (size_t)XBUF_BYTES + YBUF_BYTES + 2u * NR * sizeof(cf) + 2 * sizeof(uint64_t);   // mbarrier + arrive counter
 };
 
 // v[i] *= (or *= conj of) base0 * step^i for i in [0, NR): twiddle powers generated in registers, 8 at a time.
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
     cf* const ybuf = reinterpret_cast<cf*>(smem + C::XBUF_BYTES);                        // exchange [NT][XS]
     cf* const cj = reinterpret_cast<cf*>(smem + C::XBUF_BYTES + C::YBUF_BYTES);          // [2][NR]  W_T^{NR r f2s}
     uint64_t* const mbar = reinterpret_cast<uint64_t*>(cj + 2 * NR);                     // [1]
+    unsigned int* const xdone = reinterpret_cast<unsigned int*>(mbar + 1);               // warps that have drained X
 
     const int tid = threadIdx.x;
     const int tp = tid % P, tm2 = tid / P;      // time-side mapping
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
     if (tid == 0) {
         mbar_init(mbar, 1);
         fence_mbar_init();
+        *xdone = 0u;
     }
     __syncthreads();
     if (tid == 0) issue_load(0);
@@ -268,10 +270,18 @@ __global__ void __launch_bounds__(NR* P, MINB)
 #pragma unroll
                 for (int m1 = 0; m1 < NR; ++m1) v[m1] = PairIO<IO>::load_s(src + m1 * NR * 2 * P);
             }
+            // the last warp to drain X re-arms it with the next pass right away (X is the staging buffer after the
+            // last pass, so nothing is prefetched across the analysis/synthesis boundary)
+            if (r + 1 < R) {
+                __syncwarp();
+                if ((tid & 31) == 0) {
+                    __threadfence_block();
+                    if ((atomicAdd(xdone, 1u) % (NT / 32)) == NT / 32 - 1) issue_load(L + 1);
+                }
+            }
             Dft<NR, -1>::run(v);   // over m1 -> f1
             apply_power_twiddles<NR, false, true>(v, cf{1.f, 0.f}, cf{wb.x, wb.y});   // v[f1] *= W_T^{(R m2 + r) f1}
-            __syncthreads();   // (A) everyone has pulled the landed tile out of X; last pass's exchange reads are done
-            if (tid == 0 && r + 1 < R) issue_load(L + 1);   // X becomes the staging buffer after the last pass
+            __syncthreads();   // (A) last pass's exchange reads are done
             {
                 float4* xrow = reinterpret_cast<float4*>(ybuf + tid * XS);
 #pragma unroll
@@ -399,8 +409,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
             }
             Dft<NR, +1>::run(v);   // over f2 -> m2
             apply_power_twiddles<NR, true, false>(v, cf{sr.x, sr.y}, cf{beta.x, beta.y});
-            __syncthreads();   // (A') previous exchange readers are done; previous pass's staging rows are complete
-            if (tid == 0 && r > 0) issue_store(b, dt, r - 1);
+            __syncthreads();   // (A') previous exchange readers are done
             {
                 cf* xb = ybuf + fp2 * XS + ff1;
 #pragma unroll
@@ -425,11 +434,11 @@ __global__ void __launch_bounds__(NR* P, MINB)
                 for (int m1 = 0; m1 < NR; ++m1) PairIO<IO>::store_s(dst + m1 * NR * 2 * P, cadd(v[m1], bias2));
             }
             fence_proxy_async();
+            __syncthreads();   // (C') staging tile complete: the store drains while the next pass computes
+            if (tid == 0) issue_store(b, dt, r);
             slot ^= 1;
         }
-        __syncthreads();   // (C') last staging tile complete
         if (tid == 0) {
-            issue_store(b, dt, R - 1);
             tma_store_wait_read();
             issue_load(L);   // pass 0 of the next tile
         }
