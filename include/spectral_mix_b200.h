@@ -85,6 +85,10 @@ int sml_wirtinger_filter_backward(const void* g, const void* x_freq, const float
 /* Number of kernel launches issued by this library in the calling process so far (bench.py's gpu_launches). */
 unsigned long long sml_launch_count(void);
 
+/* Diagnostics (SML_DEBUG=1 in the environment): prints the record left by a kernel whose mbarrier wait timed out
+ * (the kernel traps instead of hanging the GPU) to stderr; returns the number of records. */
+int sml_debug_dump(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,8 @@ def _declare(lib):
     lib.sml_last_error.argtypes = []
     lib.sml_launch_count.restype = ctypes.c_ulonglong
     lib.sml_launch_count.argtypes = []
+    lib.sml_debug_dump.restype = c_int
+    lib.sml_debug_dump.argtypes = []
     lib.sml_plan.restype = c_int
     lib.sml_plan.argtypes = [c_int, c_int, c_int, c_int, c_int, ip, ip, ip, ip]
     lib.sml_xlow_bytes.restype = c_size_t
@@ -72,7 +74,7 @@ EXPORTED_SYMBOLS = (
     "sml_forward", "sml_backward",
     "sml_wirtinger_mul_forward", "sml_wirtinger_mul_backward",
     "sml_wirtinger_filter_forward", "sml_wirtinger_filter_backward",
-    "sml_launch_count",
+    "sml_launch_count", "sml_debug_dump",
 )
 
 

@@ -16,6 +16,7 @@
 
 #include "../../include/spectral_mix_b200.h"
 #include "sml_fast.cuh"
+#include "sml_fast_ws.cuh"
 #include "sml_generic.cuh"
 #include "sml_wirtinger.cuh"
 
@@ -65,6 +66,21 @@ int device_state(DeviceState** out, int* dev_out) {
     return 0;
 }
 
+// SML_DEBUG=1: a host-mapped record that a timed-out mbarrier wait fills before it traps (readable after the fault)
+unsigned int* g_dbg_host = nullptr;
+unsigned int* debug_record() {
+    static std::once_flag once;
+    static unsigned int* dev = nullptr;
+    std::call_once(once, [] {
+        const char* e = getenv("SML_DEBUG");
+        if (e == nullptr || atoi(e) == 0) return;
+        if (cudaHostAlloc(&g_dbg_host, 4096, cudaHostAllocMapped) != cudaSuccess) { g_dbg_host = nullptr; return; }
+        memset(g_dbg_host, 0, 4096);
+        if (cudaHostGetDevicePointer(&dev, g_dbg_host, 0) != cudaSuccess) dev = nullptr;
+    });
+    return dev;
+}
+
 int twiddle_table(DeviceState* st, int T, cudaStream_t stream, const sml::cf** out) {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = st->twiddles.find(T);
@@ -89,6 +105,7 @@ struct Plan {
     int k = 0;
     int NR = 0, KJ = 0, P = 0, M = 0, R = 0;
     int ctas_per_sm = 1;
+    bool ws = false;   // warp-specialised 512-thread kernel (NR = 32 only)
 };
 
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -121,8 +138,10 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
             if (const char* e = getenv("SML_FAST_CTAS")) {   // tuning knob for the NR=32, KJ=12 kernel: 2 or 3 CTAs per SM
                 if (atoi(e) == 2 && p.NR == 32 && p.KJ == 12) p.ctas_per_sm = 2;
             }
-            if (const char* e = getenv("SML_FAST_P")) {      // tuning knob: 6 pairs per CTA (48-byte TMA rows), 2 CTAs per SM
-                if (atoi(e) == 6 && p.NR == 32 && p.KJ == 12) { p.P = 6; p.ctas_per_sm = 2; }
+            if (p.NR == 32) {   // M = 1024: warp-specialised kernel, 8 pairs (64-byte TMA rows) per CTA, one CTA per SM
+                p.ws = false;   // experimental (opt-in) until it is parity-green on the GPU
+                if (const char* e = getenv("SML_FAST_WS")) p.ws = atoi(e) != 0;   // tuning knob: 1 = warp-specialised kernel
+                if (p.ws) { p.P = 8; p.ctas_per_sm = 1; }
             }
             return p;
         }
@@ -189,16 +208,37 @@ int launch_fast_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, cons
     return 0;
 }
 
+template <int KJ, typename IO, bool BWD>
+int launch_ws_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
+                   cudaStream_t stream) {
+    using C = sml::WsCfg<IO>;
+    auto kern = sml::sml_ws_kernel<KJ, IO, BWD>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    });
+    if (attr_err != cudaSuccess) return fail("cudaFuncSetAttribute(smem=%zu) failed: %s", C::SMEM_BYTES, cudaGetErrorString(attr_err));
+    kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map_in, map_out, prm);
+    count_launch();
+    SML_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <typename IO, bool BWD>
 int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm,
                 int grid, cudaStream_t stream) {
+    if (p.ws) {
+        if (p.KJ == 8) return launch_ws_inst<8, IO, BWD>(map_in, map_out, prm, grid, stream);
+        if (p.KJ == 12) return launch_ws_inst<12, IO, BWD>(map_in, map_out, prm, grid, stream);
+        return launch_ws_inst<16, IO, BWD>(map_in, map_out, prm, grid, stream);
+    }
 #define SML_CASE(NR_, KJ_, P_, MINB_) \
     if (p.NR == NR_ && p.KJ == KJ_ && p.P == P_ && p.ctas_per_sm == MINB_) return launch_fast_inst<NR_, KJ_, P_, MINB_, IO, BWD>(map_in, map_out, prm, grid, stream);
     SML_CASE(32, 8, 4, 3)
     SML_CASE(32, 12, 4, 3)
     SML_CASE(32, 16, 4, 2)
     SML_CASE(32, 12, 4, 2)
-    SML_CASE(32, 12, 6, 2)
     SML_CASE(16, 4, 8, 3)
     SML_CASE(16, 8, 8, 3)
     SML_CASE(8, 4, 32, 2)
@@ -237,6 +277,7 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
         prm.ntd = (D + 2 * p.P - 1) / (2 * p.P);
         prm.ntiles = B * prm.ntd;
         prm.invT = invT;
+        prm.dbg = debug_record();
         const int slots = st->sm_count * p.ctas_per_sm;
         const int grid = prm.ntiles < slots ? prm.ntiles : slots;
         return launch_fast<IO, false>(p, map, map_out, prm, grid, stream);
@@ -290,6 +331,7 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         prm.ntd = (D + 2 * p.P - 1) / (2 * p.P);
         prm.ntiles = B * prm.ntd;
         prm.invT = invT;
+        prm.dbg = debug_record();
         const int slots = st->sm_count * p.ctas_per_sm;
         const int grid = prm.ntiles < slots ? prm.ntiles : slots;
         return launch_fast<IO, true>(p, map, map_out, prm, grid, stream);
@@ -330,6 +372,17 @@ int sml_abi_version(void) { return 1; }
 const char* sml_last_error(void) { return g_err; }
 
 unsigned long long sml_launch_count(void) { return g_launches.load(); }
+
+int sml_debug_dump(void) {
+    if (g_dbg_host == nullptr) return 0;
+    const unsigned int n = g_dbg_host[0];
+    fprintf(stderr, "sml_debug: %u timed-out mbarrier waits recorded\n", n);
+    for (unsigned int i = 0; i < n && i < 64u; ++i) {
+        const unsigned int* r = g_dbg_host + 8 + 8 * i;
+        fprintf(stderr, "  tag=%u block=%u tid=%u parity=%u aux=%u\n", r[0], r[1], r[2], r[3], r[4]);
+    }
+    return (int)n;
+}
 
 int sml_plan(int B, int T, int D, int F, int io_dtype, int* path, int* M, int* R, int* k) {
     if (check_common(&B, &B, B, T, D, F, io_dtype)) return 1;

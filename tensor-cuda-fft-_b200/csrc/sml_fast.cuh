@@ -51,6 +51,7 @@ struct FastParams {
     int ntd;               // channel tiles = ceil(D / 2P)
     int ntiles;            // B * ntd
     float invT;
+    unsigned int* dbg;     // host-mapped debug record (null unless SML_DEBUG is set): filled by a timed-out mbarrier wait
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -69,6 +70,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -82,10 +86,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// cold path of mbar_wait: leave a record in host-mapped memory (SML_DEBUG=1), then trap
+__device__ __noinline__ void mbar_timeout(unsigned int* dbg, uint32_t tag, uint32_t parity, uint32_t aux) {
+    if (dbg != nullptr) {
+        const unsigned int slot = atomicAdd(dbg, 1u);
+        if (slot < 64u) {
+            unsigned int* r = dbg + 8 + 8 * slot;
+            r[0] = tag; r[1] = blockIdx.x; r[2] = threadIdx.x; r[3] = parity; r[4] = aux;
+        }
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg = nullptr, uint32_t tag = 0,
+                                          uint32_t aux = 0) {
     // bounded spin: a lost TMA completion becomes a trap (reported as a launch failure) instead of a hung GPU
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 26)) __trap();
+        if (spins > (1u << 24)) mbar_timeout(dbg, tag, parity, aux);
     }
 }
 // 4-D tiled TMA load global -> shared, completion signalled on an mbarrier (SASS: UTMALDG)
@@ -184,6 +201,86 @@ __device__ __forceinline__ void apply_power_twiddles(cf (&v)[NR], const cf base0
 }
 
 // ------------------------------------------------------------------------------------------------
+// mid phase (freq-side threads): acc holds the two-sided band Z of z = x_d + i x_{d+1}; on return it holds the band
+// C whose inverse transform is y_d + i y_{d+1}.  Hermitian split through warp shuffles (the partner bin -f lives in
+// lane NR - f1 of the same warp), complex filter (reference spectral_layers.py:101-105), and for BWD the Wirtinger
+// filter gradient G conj(X) (reference wirtinger_ops.py:77-80) reduced over the batch with fp32 atomics.
+// ------------------------------------------------------------------------------------------------
+template <int NR, int KJ, bool BWD>
+__device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const FastParams& prm, int b, int d0, int ff1, int lane) {
+    constexpr int NJ = 2 * KJ;
+    const int D = prm.D;
+    const bool pvalid = d0 < D;
+    const int src_lane = (lane & ~(NR - 1)) | ((NR - ff1) & (NR - 1));
+    cf part[NJ];   // value of the band at -fs
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int pj = NJ - 1 - j;
+        const int pj0 = (NJ - j) % NJ;
+        float pre = __shfl_sync(0xffffffffu, acc[pj].re, src_lane);
+        float pim = __shfl_sync(0xffffffffu, acc[pj].im, src_lane);
+        if (ff1 == 0) {
+            pre = acc[pj0].re;
+            pim = acc[pj0].im;
+        }
+        part[j] = cf{pre, pim};
+    }
+    const size_t wrow0 = (size_t)d0 * prm.F, wrow1 = wrow0 + prm.F;
+    const size_t xrow0 = ((size_t)b * D + d0) * prm.k, xrow1 = xrow0 + prm.k;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const bool pos = j < KJ;
+        const int fs = pos ? ff1 + NR * j : ff1 + NR * (j - NJ);
+        const int af = fs < 0 ? -fs : fs;
+        const bool live = pvalid && af < prm.k;
+        const cf zp = pos ? acc[j] : part[j];
+        const cf zm = pos ? part[j] : acc[j];
+        // Hermitian split: spectra of the two real channels at +af
+        const cf s0 = cf{0.5f * (zp.re + zm.re), 0.5f * (zp.im - zm.im)};
+        const cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
+        cf w0 = cf{0.f, 0.f}, w1 = cf{0.f, 0.f};
+        if (live) {
+            w0 = cf{__ldg(prm.w_re + wrow0 + af), __ldg(prm.w_im + wrow0 + af)};
+            w1 = cf{__ldg(prm.w_re + wrow1 + af), __ldg(prm.w_im + wrow1 + af)};
+        }
+        cf a0, a1;
+        if constexpr (!BWD) {
+            if (pos && live && prm.xlow != nullptr) {
+                reinterpret_cast<float2*>(prm.xlow)[xrow0 + af] = make_float2(s0.re, s0.im);
+                reinterpret_cast<float2*>(prm.xlow)[xrow1 + af] = make_float2(s1.re, s1.im);
+            }
+            a0 = cmul(s0, w0);
+            a1 = cmul(s1, w1);
+        } else {
+            if (pos && live && prm.gw_re != nullptr) {
+                const float2 x0 = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
+                const float2 x1 = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
+                const cf g0 = cmulc(s0, cf{x0.x, x0.y});   // G conj(X)
+                const cf g1 = cmulc(s1, cf{x1.x, x1.y});
+                atomicAdd(prm.gw_re + wrow0 + af, g0.re * prm.invT);
+                atomicAdd(prm.gw_im + wrow0 + af, g0.im * prm.invT);
+                atomicAdd(prm.gw_re + wrow1 + af, g1.re * prm.invT);
+                atomicAdd(prm.gw_im + wrow1 + af, g1.im * prm.invT);
+                if (fs == 0) {
+                    atomicAdd(prm.gb + d0, s0.re);
+                    atomicAdd(prm.gb + d0 + 1, s1.re);
+                }
+            }
+            a0 = cmulc(s0, w0);   // G conj(W)
+            a1 = cmulc(s1, w1);
+        }
+        cf c;
+        if (pos) {
+            c = cf{0.5f * (a0.re - a1.im), 0.5f * (a0.im + a1.re)};
+            if (j == 0 && ff1 == 0) c = cf{a0.re, a1.re};   // DC bin
+        } else {
+            c = cf{0.5f * (a0.re + a1.im), 0.5f * (a1.re - a0.im)};
+        }
+        acc[j] = cf{c.re * prm.invT, c.im * prm.invT};
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int NR, int KJ, int P, int MINB, typename IO, bool BWD>
@@ -263,7 +360,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
                 cjv = cj_load(r);
                 if (r + 1 == R) cjn = cj_load(0);   // first synthesis pass
             }
-            mbar_wait(mbar, (uint32_t)L & 1u);
+            mbar_wait(mbar, (uint32_t)L & 1u, prm.dbg, 1u, (uint32_t)L);
             cf v[NR];
             {
                 const IO* src = reinterpret_cast<const IO*>(xbuf) + tm2 * 2 * P + 2 * tp;
@@ -311,78 +408,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
         }
 
         // ===================== mid phase: un-mix the channel pair, filter, re-pack =====================
-        const int d0 = dt * 2 * P + 2 * fp2;   // freq-side channel pair
-        const bool pvalid = d0 < D;
-        {
-            const int lane = tid & 31;
-            const int src_lane = (lane & ~(NR - 1)) | ((NR - ff1) & (NR - 1));
-            cf part[NJ];   // value of the band at -fs
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int pj = NJ - 1 - j;
-                const int pj0 = (NJ - j) % NJ;
-                float pre = __shfl_sync(0xffffffffu, acc[pj].re, src_lane);
-                float pim = __shfl_sync(0xffffffffu, acc[pj].im, src_lane);
-                if (ff1 == 0) {
-                    pre = acc[pj0].re;
-                    pim = acc[pj0].im;
-                }
-                part[j] = cf{pre, pim};
-            }
-            const size_t wrow0 = (size_t)d0 * prm.F, wrow1 = wrow0 + prm.F;
-            const size_t xrow0 = ((size_t)b * D + d0) * prm.k, xrow1 = xrow0 + prm.k;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const bool pos = j < KJ;
-                const int fs = pos ? ff1 + NR * j : ff1 + NR * (j - NJ);
-                const int af = fs < 0 ? -fs : fs;
-                const bool live = pvalid && af < prm.k;
-                const cf zp = pos ? acc[j] : part[j];
-                const cf zm = pos ? part[j] : acc[j];
-                // Hermitian split: spectra of the two real channels at +af
-                const cf s0 = cf{0.5f * (zp.re + zm.re), 0.5f * (zp.im - zm.im)};
-                const cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
-                cf w0 = cf{0.f, 0.f}, w1 = cf{0.f, 0.f};
-                if (live) {
-                    w0 = cf{__ldg(prm.w_re + wrow0 + af), __ldg(prm.w_im + wrow0 + af)};
-                    w1 = cf{__ldg(prm.w_re + wrow1 + af), __ldg(prm.w_im + wrow1 + af)};
-                }
-                cf a0, a1;
-                if constexpr (!BWD) {
-                    if (pos && live && prm.xlow != nullptr) {
-                        reinterpret_cast<float2*>(prm.xlow)[xrow0 + af] = make_float2(s0.re, s0.im);
-                        reinterpret_cast<float2*>(prm.xlow)[xrow1 + af] = make_float2(s1.re, s1.im);
-                    }
-                    a0 = cmul(s0, w0);
-                    a1 = cmul(s1, w1);
-                } else {
-                    if (pos && live && prm.gw_re != nullptr) {
-                        const float2 x0 = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
-                        const float2 x1 = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
-                        const cf g0 = cmulc(s0, cf{x0.x, x0.y});   // G conj(X)
-                        const cf g1 = cmulc(s1, cf{x1.x, x1.y});
-                        atomicAdd(prm.gw_re + wrow0 + af, g0.re * prm.invT);
-                        atomicAdd(prm.gw_im + wrow0 + af, g0.im * prm.invT);
-                        atomicAdd(prm.gw_re + wrow1 + af, g1.re * prm.invT);
-                        atomicAdd(prm.gw_im + wrow1 + af, g1.im * prm.invT);
-                        if (fs == 0) {
-                            atomicAdd(prm.gb + d0, s0.re);
-                            atomicAdd(prm.gb + d0 + 1, s1.re);
-                        }
-                    }
-                    a0 = cmulc(s0, w0);   // G conj(W)
-                    a1 = cmulc(s1, w1);
-                }
-                cf c;
-                if (pos) {
-                    c = cf{0.5f * (a0.re - a1.im), 0.5f * (a0.im + a1.re)};
-                    if (j == 0 && ff1 == 0) c = cf{a0.re, a1.re};   // DC bin
-                } else {
-                    c = cf{0.5f * (a0.re + a1.im), 0.5f * (a1.re - a0.im)};
-                }
-                acc[j] = cf{c.re * prm.invT, c.im * prm.invT};
-            }
-        }
+        spectral_mid_phase<NR, KJ, BWD>(acc, prm, b, dt * 2 * P + 2 * fp2, ff1, tid & 31);
 
         // ===================== synthesis: transpose of analysis; rows leave through a TMA store from X =====================
         const int td0 = dt * 2 * P + 2 * tp;   // time-side channel pair

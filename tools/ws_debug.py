@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""GPU diagnostic: run the warp-specialised kernel (SML_FAST_WS=1) against the lockstep kernel on multi-tile shapes.
+On a trap, print the mbarrier-timeout record (SML_DEBUG=1).  usage: SML_DEBUG=1 python tools/ws_debug.py"""
+import os, sys, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("SML_DEBUG", "1")
+import torch
+from tensor_cuda_fft_b200 import _native
+
+lib = _native.lib()
+dev = torch.device("cuda:0")
+shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]] or [(1, 1024, 768), (4, 1024, 768), (4, 2048, 768), (16, 8192, 768)]
+for (B, T, D) in shapes:
+    Fn = D // 2
+    torch.manual_seed(0)
+    x = torch.randn(B, T, D, device=dev)
+    g = torch.randn(B, T, D, device=dev)
+    wr, wi, bs = torch.randn(D, Fn, device=dev), torch.randn(D, Fn, device=dev), torch.randn(D, device=dev)
+    res = {}
+    for ws in ("0", "1"):
+        os.environ["SML_FAST_WS"] = ws
+        y, gx = torch.empty_like(x), torch.empty_like(x)
+        xlow = torch.empty(lib.sml_xlow_bytes(B, T, D, Fn), dtype=torch.uint8, device=dev)
+        gwr, gwi, gb = torch.empty(D, Fn, device=dev), torch.empty(D, Fn, device=dev), torch.empty(D, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        try:
+            _native.check(lib.sml_forward(x.data_ptr(), wr.data_ptr(), wi.data_ptr(), bs.data_ptr(), y.data_ptr(), xlow.data_ptr(), B, T, D, Fn, 0, st))
+            torch.cuda.synchronize()
+            print(f"{(B, T, D)} ws={ws} fwd ok", flush=True)
+            _native.check(lib.sml_backward(g.data_ptr(), xlow.data_ptr(), wr.data_ptr(), wi.data_ptr(), gx.data_ptr(), gwr.data_ptr(), gwi.data_ptr(), gb.data_ptr(), None, 0, B, T, D, Fn, 0, st))
+            torch.cuda.synchronize()
+            print(f"{(B, T, D)} ws={ws} bwd ok", flush=True)
+        except Exception as e:
+            print(f"{(B, T, D)} ws={ws} FAILED: {str(e).splitlines()[0]}", flush=True)
+            lib.sml_debug_dump()
+            sys.exit(1)
+        res[ws] = (y, gx, gwr, gwi, gb)
+    for name, a, b in zip(("y", "gx", "gw_re", "gw_im", "gb"), res["0"], res["1"]):
+        err = ((a - b).norm() / b.norm()).item()
+        print(f"   {name}: rel-L2(ws1 vs ws0) = {err:.3e}")
+print("ws_debug done")
