@@ -64,6 +64,17 @@ int sml_backward(const void* g, const void* xlow, const float* w_re, const float
                  float* gw_re, float* gw_im, float* gb, void* workspace, size_t workspace_bytes, int B, int T,
                  int D, int F, int io_dtype, void* stream);
 
+/* Forward + backward over HOST buffers (pinned memory recommended: pageable memory serialises the copies).
+ * Same math as sml_forward followed by sml_backward, for hosts whose activations live in CPU memory: the batch is cut
+ * into chunks of `chunk_batch` elements (0 = choose) and the host->device copy of chunk i+1, the two kernels of
+ * chunk i and the device->host copy of chunk i-1 overlap on three internal streams.  All pointers are HOST pointers;
+ * x, g, y, gx: (B, T, D) in io_dtype; w_re, w_im, gw_re, gw_im: (D, F) fp32; bias, gb: (D,) fp32.  bias may be NULL;
+ * gw_re = gw_im = gb = NULL skips the filter gradient.  Synchronous: returns when every output is in host memory.
+ * Runs on the current CUDA device; device staging buffers are cached between calls. */
+int sml_fwd_bwd_host(const void* x, const void* g, const float* w_re, const float* w_im, const float* bias, void* y,
+                     void* gx, float* gw_re, float* gw_im, float* gb, int B, int T, int D, int F, int io_dtype,
+                     int chunk_batch);
+
 /* Wirtinger filter multiply on an already transformed tensor.
  * Replaces WirtingerGradient.forward / .backward, wirtinger_ops.py:34-50 / :53-82.
  * x, g, out, gx: (B, N) complex64 (interleaved re,im); w, gw: (N,) complex64 broadcast over B.

@@ -3,13 +3,14 @@
 Public surface mirrors the reference modules ``fft_tensor.spectral_layers`` and ``fft_tensor.wirtinger_ops``.
 """
 from . import _native
-from .spectral_layers import (HybridSpectralAttention, SpectralMLPBlock, SpectralMixingLayer, spectral_mix)
+from .spectral_layers import (HybridSpectralAttention, SpectralMLPBlock, SpectralMixingLayer, spectral_mix,
+                              spectral_mix_fwd_bwd_host)
 from .wirtinger_ops import (ComplexParameter, WirtingerGradient, WirtingerSpectralFilter)
 from .distributed import allreduce_filter_grads, shard_batch
 
 __version__ = "0.1.0"
 __all__ = [
-    "SpectralMixingLayer", "SpectralMLPBlock", "HybridSpectralAttention", "spectral_mix",
+    "SpectralMixingLayer", "SpectralMLPBlock", "HybridSpectralAttention", "spectral_mix", "spectral_mix_fwd_bwd_host",
     "WirtingerGradient", "ComplexParameter", "WirtingerSpectralFilter",
     "allreduce_filter_grads", "shard_batch",
 ]

@@ -15,8 +15,7 @@
 #include <utility>
 
 #include "../../include/spectral_mix_b200.h"
-#include "sml_fast.cuh"
-#include "sml_fast_ws.cuh"
+#include "sml_host.h"
 #include "sml_generic.cuh"
 #include "sml_wirtinger.cuh"
 
@@ -25,6 +24,9 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 
+}   // namespace
+
+namespace sml_host {
 int fail(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -32,6 +34,14 @@ int fail(const char* fmt, ...) {
     va_end(ap);
     return 1;
 }
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+}   // namespace sml_host
+
+namespace {
+using sml_host::count_launch;
+using sml_host::fail;
+using sml_host::launch_fast;
+using sml_host::Plan;
 
 #define SML_CUDA(expr)                                                                         \
     do {                                                                                       \
@@ -39,7 +49,6 @@ int fail(const char* fmt, ...) {
         if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e));    \
     } while (0)
 
-inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------------
 // per-device state
@@ -74,8 +83,8 @@ unsigned int* debug_record() {
     std::call_once(once, [] {
         const char* e = getenv("SML_DEBUG");
         if (e == nullptr || atoi(e) == 0) return;
-        if (cudaHostAlloc(&g_dbg_host, 4096, cudaHostAllocMapped) != cudaSuccess) { g_dbg_host = nullptr; return; }
-        memset(g_dbg_host, 0, 4096);
+        if (cudaHostAlloc(&g_dbg_host, 8192, cudaHostAllocMapped) != cudaSuccess) { g_dbg_host = nullptr; return; }
+        memset(g_dbg_host, 0, 8192);
         if (cudaHostGetDevicePointer(&dev, g_dbg_host, 0) != cudaSuccess) dev = nullptr;
     });
     return dev;
@@ -100,14 +109,6 @@ int twiddle_table(DeviceState* st, int T, cudaStream_t stream, const sml::cf** o
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-struct Plan {
-    int path = SML_PATH_GENERIC;
-    int k = 0;
-    int NR = 0, KJ = 0, P = 0, M = 0, R = 0;
-    int ctas_per_sm = 1;
-    bool ws = false;   // warp-specialised 512-thread kernel (NR = 32 only)
-};
-
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 Plan make_plan(int T, int D, int F, int io_dtype) {
@@ -188,64 +189,6 @@ int encode_act_map(CUtensorMap* map, const void* base, int B, int T, int D, int 
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// fast-path launch
-// ------------------------------------------------------------------------------------------------
-template <int NR, int KJ, int P, int MINB, typename IO, bool BWD>
-int launch_fast_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
-                     cudaStream_t stream) {
-    using C = sml::FastCfg<NR, P, IO>;
-    auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD>;
-    static std::once_flag once;   // one per instantiation
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-    });
-    if (attr_err != cudaSuccess) return fail("cudaFuncSetAttribute(smem=%zu) failed: %s", C::SMEM_BYTES, cudaGetErrorString(attr_err));
-    kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map_in, map_out, prm);
-    count_launch();
-    SML_CUDA(cudaGetLastError());
-    return 0;
-}
-
-template <int KJ, typename IO, bool BWD>
-int launch_ws_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
-                   cudaStream_t stream) {
-    using C = sml::WsCfg<IO>;
-    auto kern = sml::sml_ws_kernel<KJ, IO, BWD>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-    });
-    if (attr_err != cudaSuccess) return fail("cudaFuncSetAttribute(smem=%zu) failed: %s", C::SMEM_BYTES, cudaGetErrorString(attr_err));
-    kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map_in, map_out, prm);
-    count_launch();
-    SML_CUDA(cudaGetLastError());
-    return 0;
-}
-
-template <typename IO, bool BWD>
-int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm,
-                int grid, cudaStream_t stream) {
-    if (p.ws) {
-        if (p.KJ == 8) return launch_ws_inst<8, IO, BWD>(map_in, map_out, prm, grid, stream);
-        if (p.KJ == 12) return launch_ws_inst<12, IO, BWD>(map_in, map_out, prm, grid, stream);
-        return launch_ws_inst<16, IO, BWD>(map_in, map_out, prm, grid, stream);
-    }
-#define SML_CASE(NR_, KJ_, P_, MINB_) \
-    if (p.NR == NR_ && p.KJ == KJ_ && p.P == P_ && p.ctas_per_sm == MINB_) return launch_fast_inst<NR_, KJ_, P_, MINB_, IO, BWD>(map_in, map_out, prm, grid, stream);
-    SML_CASE(32, 8, 4, 3)
-    SML_CASE(32, 12, 4, 3)
-    SML_CASE(32, 16, 4, 2)
-    SML_CASE(32, 12, 4, 2)
-    SML_CASE(16, 4, 8, 3)
-    SML_CASE(16, 8, 8, 3)
-    SML_CASE(8, 4, 32, 2)
-#undef SML_CASE
-    return fail("internal: no fast kernel for NR=%d KJ=%d P=%d", p.NR, p.KJ, p.P);
-}
-
 int check_common(const void* a, const void* b, int B, int T, int D, int F, int io_dtype) {
     if (a == nullptr || b == nullptr) return fail("null activation pointer");
     if (B < 1 || T < 1 || D < 1 || F < 1) return fail("invalid shape B=%d T=%d D=%d F=%d", B, T, D, F);
@@ -315,9 +258,14 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
     const bool aligned = ((uintptr_t)g % 16 == 0) && ((uintptr_t)gx % 16 == 0);
     if (p.path == SML_PATH_FAST && aligned) {
         if (want_grads) {
-            SML_CUDA(cudaMemsetAsync(gw_re, 0, sizeof(float) * (size_t)D * F, stream));
-            SML_CUDA(cudaMemsetAsync(gw_im, 0, sizeof(float) * (size_t)D * F, stream));
-            SML_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)D, stream));
+            const size_t nW = (size_t)D * F;
+            if (gw_im == gw_re + nW && gb == gw_im + nW) {   // one flat [gw_re | gw_im | gb] buffer (the host module's layout)
+                SML_CUDA(cudaMemsetAsync(gw_re, 0, sizeof(float) * (2 * nW + (size_t)D), stream));
+            } else {
+                SML_CUDA(cudaMemsetAsync(gw_re, 0, sizeof(float) * nW, stream));
+                SML_CUDA(cudaMemsetAsync(gw_im, 0, sizeof(float) * nW, stream));
+                SML_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)D, stream));
+            }
         }
         CUtensorMap map, map_out;
         if (encode_act_map(&map, g, B, T, D, io_dtype, p)) return 1;
@@ -360,6 +308,154 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer pipeline: fwd+bwd over HOST tensors, chunked along the batch axis so that the H2D copy of chunk i+1,
+// the kernels of chunk i and the D2H copy of chunk i-1 overlap (three streams, NBUF device slots).
+// ------------------------------------------------------------------------------------------------
+__global__ void accumulate_kernel(float* __restrict__ total, const float* __restrict__ part, size_t n, int first) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        total[i] = first ? part[i] : total[i] + part[i];
+}
+
+struct HostPipe {
+    static constexpr int NBUF = 3;
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[NBUF] = {}, ev_cmp[NBUF] = {}, ev_out[NBUF] = {};
+    char* act[NBUF][4] = {};   // x, g, y, gx
+    char* xlow[NBUF] = {};
+    char* ws[NBUF] = {};
+    float* params = nullptr;       // [w_re | w_im | bias]
+    float* grad_part = nullptr;    // [gw_re | gw_im | gb] of one chunk
+    float* grad_total = nullptr;
+    size_t cap_act = 0, cap_xlow = 0, cap_ws = 0, cap_par = 0;
+    bool ready = false;
+};
+std::mutex g_pipe_mu;
+std::map<int, HostPipe> g_pipes;
+
+int pipe_reserve(HostPipe& hp, size_t act_bytes, size_t xlow_bytes, size_t ws_bytes, size_t par_floats) {
+    if (!hp.ready) {
+        SML_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+        SML_CUDA(cudaStreamCreateWithFlags(&hp.s_cmp, cudaStreamNonBlocking));
+        SML_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < HostPipe::NBUF; ++i) {
+            SML_CUDA(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
+            SML_CUDA(cudaEventCreateWithFlags(&hp.ev_cmp[i], cudaEventDisableTiming));
+            SML_CUDA(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
+        }
+        hp.ready = true;
+    }
+    auto grow = [](char** p, size_t* cap, size_t need) -> cudaError_t {
+        if (need <= *cap && *p != nullptr) return cudaSuccess;
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        cudaError_t e = cudaMalloc(p, need > 0 ? need : 256);
+        if (e == cudaSuccess) *cap = need;
+        return e;
+    };
+    if (act_bytes > hp.cap_act || hp.act[0][0] == nullptr) {
+        SML_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < HostPipe::NBUF; ++i)
+            for (int j = 0; j < 4; ++j) {
+                size_t cap = 0;
+                SML_CUDA(grow(&hp.act[i][j], &cap, act_bytes));
+            }
+        hp.cap_act = act_bytes;
+    }
+    if (xlow_bytes > hp.cap_xlow || hp.xlow[0] == nullptr) {
+        SML_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < HostPipe::NBUF; ++i) { size_t cap = 0; SML_CUDA(grow(&hp.xlow[i], &cap, xlow_bytes)); }
+        hp.cap_xlow = xlow_bytes;
+    }
+    if (ws_bytes > hp.cap_ws || hp.ws[0] == nullptr) {
+        SML_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < HostPipe::NBUF; ++i) { size_t cap = 0; SML_CUDA(grow(&hp.ws[i], &cap, ws_bytes)); }
+        hp.cap_ws = ws_bytes;
+    }
+    if (par_floats > hp.cap_par || hp.params == nullptr) {
+        SML_CUDA(cudaDeviceSynchronize());
+        size_t c0 = 0, c1 = 0, c2 = 0;
+        SML_CUDA(grow(reinterpret_cast<char**>(&hp.params), &c0, par_floats * sizeof(float)));
+        SML_CUDA(grow(reinterpret_cast<char**>(&hp.grad_part), &c1, par_floats * sizeof(float)));
+        SML_CUDA(grow(reinterpret_cast<char**>(&hp.grad_total), &c2, par_floats * sizeof(float)));
+        hp.cap_par = par_floats;
+    }
+    return 0;
+}
+
+template <typename IO>
+int fwd_bwd_host_impl(const void* x, const void* g, const float* w_re, const float* w_im, const float* bias, void* y,
+                      void* gx, float* gw_re, float* gw_im, float* gb, int B, int T, int D, int F, int io_dtype,
+                      int chunk_batch) {
+    int dev = 0;
+    SML_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_pipe_mu);   // one host-pipeline call per device at a time
+    HostPipe& hp = g_pipes[dev];
+    const size_t esz = sizeof(IO);
+    const size_t row_bytes = (size_t)T * D * esz;                 // one batch element
+    int cb = chunk_batch;
+    if (cb <= 0) {   // about 32 MB of activations per chunk and at least 4 chunks when the batch allows it
+        cb = (int)((32u << 20) / row_bytes);
+        if (cb < 1) cb = 1;
+        if (cb > (B + 3) / 4) cb = (B + 3) / 4;
+        if (cb < 1) cb = 1;
+    }
+    if (cb > B) cb = B;
+    const size_t nW = (size_t)D * F, nP = 2 * nW + D;
+    const bool want_grads = gw_re != nullptr;
+    if (want_grads && (gw_im == nullptr || gb == nullptr)) return fail("gw_re, gw_im and gb must be given together");
+    if (pipe_reserve(hp, (size_t)cb * row_bytes, sml_xlow_bytes(cb, T, D, F), sml_workspace_bytes(cb, T, D, F, io_dtype), nP))
+        return 1;
+    float* d_wre = hp.params;
+    float* d_wim = hp.params + nW;
+    float* d_bias = bias ? hp.params + 2 * nW : nullptr;
+    SML_CUDA(cudaMemcpyAsync(d_wre, w_re, nW * sizeof(float), cudaMemcpyHostToDevice, hp.s_cmp));
+    SML_CUDA(cudaMemcpyAsync(d_wim, w_im, nW * sizeof(float), cudaMemcpyHostToDevice, hp.s_cmp));
+    if (bias) SML_CUDA(cudaMemcpyAsync(d_bias, bias, (size_t)D * sizeof(float), cudaMemcpyHostToDevice, hp.s_cmp));
+    const int nchunks = (B + cb - 1) / cb;
+    for (int i = 0; i < nchunks; ++i) {
+        const int s = i % HostPipe::NBUF;
+        const int b0 = i * cb, nb = (B - b0 < cb) ? B - b0 : cb;
+        const size_t off = (size_t)b0 * row_bytes, bytes = (size_t)nb * row_bytes;
+        char *dx = hp.act[s][0], *dg = hp.act[s][1], *dy = hp.act[s][2], *dgx = hp.act[s][3];
+        // H2D: the slot's x/g are free once the kernels of chunk i - NBUF have run
+        if (i >= HostPipe::NBUF) SML_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_cmp[s], 0));
+        SML_CUDA(cudaMemcpyAsync(dx, (const char*)x + off, bytes, cudaMemcpyHostToDevice, hp.s_in));
+        SML_CUDA(cudaMemcpyAsync(dg, (const char*)g + off, bytes, cudaMemcpyHostToDevice, hp.s_in));
+        SML_CUDA(cudaEventRecord(hp.ev_in[s], hp.s_in));
+        // kernels: wait for the inputs and for the slot's y/gx to have left (D2H of chunk i - NBUF)
+        SML_CUDA(cudaStreamWaitEvent(hp.s_cmp, hp.ev_in[s], 0));
+        if (i >= HostPipe::NBUF) SML_CUDA(cudaStreamWaitEvent(hp.s_cmp, hp.ev_out[s], 0));
+        if (forward_impl<IO>(dx, d_wre, d_wim, d_bias, dy, want_grads || hp.cap_ws ? hp.xlow[s] : nullptr, nb, T, D, F,
+                             io_dtype, hp.s_cmp))
+            return 1;
+        float* pg = want_grads ? hp.grad_part : nullptr;
+        if (backward_impl<IO>(dg, want_grads ? hp.xlow[s] : nullptr, d_wre, d_wim, dgx, pg, pg ? pg + nW : nullptr,
+                              pg ? pg + 2 * nW : nullptr, hp.ws[s], hp.cap_ws, nb, T, D, F, io_dtype, hp.s_cmp))
+            return 1;
+        if (want_grads) {
+            accumulate_kernel<<<148, 256, 0, hp.s_cmp>>>(hp.grad_total, hp.grad_part, nP, i == 0);
+            count_launch();
+        }
+        SML_CUDA(cudaEventRecord(hp.ev_cmp[s], hp.s_cmp));
+        // D2H
+        SML_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_cmp[s], 0));
+        SML_CUDA(cudaMemcpyAsync((char*)y + off, dy, bytes, cudaMemcpyDeviceToHost, hp.s_out));
+        SML_CUDA(cudaMemcpyAsync((char*)gx + off, dgx, bytes, cudaMemcpyDeviceToHost, hp.s_out));
+        SML_CUDA(cudaEventRecord(hp.ev_out[s], hp.s_out));
+    }
+    if (want_grads) {   // s_out already waits for the last chunk's kernels
+        SML_CUDA(cudaMemcpyAsync(gw_re, hp.grad_total, nW * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
+        SML_CUDA(cudaMemcpyAsync(gw_im, hp.grad_total + nW, nW * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
+        SML_CUDA(cudaMemcpyAsync(gb, hp.grad_total + 2 * nW, (size_t)D * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
+    }
+    SML_CUDA(cudaStreamSynchronize(hp.s_out));
+    SML_CUDA(cudaStreamSynchronize(hp.s_cmp));
+    SML_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }   // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -377,9 +473,14 @@ int sml_debug_dump(void) {
     if (g_dbg_host == nullptr) return 0;
     const unsigned int n = g_dbg_host[0];
     fprintf(stderr, "sml_debug: %u timed-out mbarrier waits recorded\n", n);
-    for (unsigned int i = 0; i < n && i < 64u; ++i) {
-        const unsigned int* r = g_dbg_host + 8 + 8 * i;
-        fprintf(stderr, "  tag=%u block=%u tid=%u parity=%u aux=%u\n", r[0], r[1], r[2], r[3], r[4]);
+    for (unsigned int t = 0; t < 31u; ++t) {
+        const unsigned int cnt = g_dbg_host[1 + t];
+        if (cnt == 0) continue;
+        fprintf(stderr, "  tag %u: %u waits\n", t, cnt);
+        for (unsigned int i = 0; i < cnt && i < 4u; ++i) {
+            const unsigned int* r = g_dbg_host + 32 + 8 * (4 * t + i);
+            fprintf(stderr, "    block=%u tid=%u parity=%u aux=%u\n", r[1], r[2], r[3], r[4]);
+        }
     }
     return (int)n;
 }
@@ -426,6 +527,18 @@ int sml_backward(const void* g, const void* xlow, const float* w_re, const float
                                     io_dtype, (cudaStream_t)stream);
     return backward_impl<__nv_bfloat16>(g, xlow, w_re, w_im, gx, gw_re, gw_im, gb, workspace, workspace_bytes, B, T, D,
                                         F, io_dtype, (cudaStream_t)stream);
+}
+
+int sml_fwd_bwd_host(const void* x, const void* g, const float* w_re, const float* w_im, const float* bias, void* y,
+                     void* gx, float* gw_re, float* gw_im, float* gb, int B, int T, int D, int F, int io_dtype,
+                     int chunk_batch) {
+    if (check_common(x, y, B, T, D, F, io_dtype)) return 1;
+    if (g == nullptr || gx == nullptr) return fail("null activation pointer");
+    if (w_re == nullptr || w_im == nullptr) return fail("null filter pointer");
+    g_err[0] = 0;
+    if (io_dtype == SML_DTYPE_F32)
+        return fwd_bwd_host_impl<float>(x, g, w_re, w_im, bias, y, gx, gw_re, gw_im, gb, B, T, D, F, io_dtype, chunk_batch);
+    return fwd_bwd_host_impl<__nv_bfloat16>(x, g, w_re, w_im, bias, y, gx, gw_re, gw_im, gb, B, T, D, F, io_dtype, chunk_batch);
 }
 
 int sml_wirtinger_mul_forward(const void* x, const void* w, void* out, long long B, long long N, void* stream) {

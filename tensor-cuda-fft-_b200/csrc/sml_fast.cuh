@@ -87,11 +87,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // cold path of mbar_wait: leave a record in host-mapped memory (SML_DEBUG=1), then trap
-__device__ __noinline__ void mbar_timeout(unsigned int* dbg, uint32_t tag, uint32_t parity, uint32_t aux) {
-    if (dbg != nullptr) {
-        const unsigned int slot = atomicAdd(dbg, 1u);
-        if (slot < 64u) {
-            unsigned int* r = dbg + 8 + 8 * slot;
+static __device__ __noinline__ void mbar_timeout(unsigned int* dbg, uint32_t tag, uint32_t parity, uint32_t aux) {
+    if (dbg != nullptr) {   // layout: [0] total, [1..31] count per tag, records of 8 words from word 32: 4 per tag
+        atomicAdd(dbg, 1u);
+        const unsigned int n = atomicAdd(dbg + 1 + (tag & 31u) % 31u, 1u);
+        if (n < 4u) {
+            unsigned int* r = dbg + 32 + 8 * (4 * ((tag & 31u) % 31u) + n);
             r[0] = tag; r[1] = blockIdx.x; r[2] = threadIdx.x; r[3] = parity; r[4] = aux;
         }
         __threadfence_system();
@@ -200,6 +201,22 @@ __device__ __forceinline__ void apply_power_twiddles(cf (&v)[NR], const cf base0
     }
 }
 
+// BWD: pull this tile's X_low rows (read once per tile in the mid phase, cold in HBM) into L2 while the analysis
+// passes run.  One lane per 128-byte line.
+template <int NR, int KJ>
+__device__ __forceinline__ void prefetch_xlow_l2(const FastParams& prm, int b, int d0, int ff1) {
+    if (prm.gw_re == nullptr || prm.xlow == nullptr || d0 >= prm.D || (ff1 & 15) != 0) return;
+    const float2* row0 = reinterpret_cast<const float2*>(prm.xlow) + ((size_t)b * prm.D + d0) * prm.k;
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+        const int af = ff1 + NR * j;
+        if (af < prm.k) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row0 + af));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row0 + prm.k + af));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // mid phase (freq-side threads): acc holds the two-sided band Z of z = x_d + i x_{d+1}; on return it holds the band
 // C whose inverse transform is y_d + i y_{d+1}.  Hermitian split through warp shuffles (the partner bin -f lives in
@@ -211,30 +228,22 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
     constexpr int NJ = 2 * KJ;
     const int D = prm.D;
     const bool pvalid = d0 < D;
+    // the bin -fs of (ff1, j) lives in lane NR - ff1 of the same warp at index NJ - 1 - j (ff1 = 0: own index NJ - j)
     const int src_lane = (lane & ~(NR - 1)) | ((NR - ff1) & (NR - 1));
-    cf part[NJ];   // value of the band at -fs
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const int pj = NJ - 1 - j;
-        const int pj0 = (NJ - j) % NJ;
-        float pre = __shfl_sync(0xffffffffu, acc[pj].re, src_lane);
-        float pim = __shfl_sync(0xffffffffu, acc[pj].im, src_lane);
-        if (ff1 == 0) {
-            pre = acc[pj0].re;
-            pim = acc[pj0].im;
-        }
-        part[j] = cf{pre, pim};
-    }
     const size_t wrow0 = (size_t)d0 * prm.F, wrow1 = wrow0 + prm.F;
     const size_t xrow0 = ((size_t)b * D + d0) * prm.k, xrow1 = xrow0 + prm.k;
+    cf cneg[KJ];   // filtered, re-packed value for the mirror bin -fs (handed back to its owner below)
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const bool pos = j < KJ;
-        const int fs = pos ? ff1 + NR * j : ff1 + NR * (j - NJ);
-        const int af = fs < 0 ? -fs : fs;
+    for (int j = 0; j < KJ; ++j) {
+        const int af = ff1 + NR * j;   // fs >= 0: each thread filters its KJ non-negative bins and serves the mirrors
         const bool live = pvalid && af < prm.k;
-        const cf zp = pos ? acc[j] : part[j];
-        const cf zm = pos ? part[j] : acc[j];
+        float mre = __shfl_sync(0xffffffffu, acc[NJ - 1 - j].re, src_lane);
+        float mim = __shfl_sync(0xffffffffu, acc[NJ - 1 - j].im, src_lane);
+        if (ff1 == 0) {
+            mre = acc[(NJ - j) % NJ].re;
+            mim = acc[(NJ - j) % NJ].im;
+        }
+        const cf zp = acc[j], zm = cf{mre, mim};
         // Hermitian split: spectra of the two real channels at +af
         const cf s0 = cf{0.5f * (zp.re + zm.re), 0.5f * (zp.im - zm.im)};
         const cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
@@ -245,14 +254,14 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
         }
         cf a0, a1;
         if constexpr (!BWD) {
-            if (pos && live && prm.xlow != nullptr) {
+            if (live && prm.xlow != nullptr) {
                 reinterpret_cast<float2*>(prm.xlow)[xrow0 + af] = make_float2(s0.re, s0.im);
                 reinterpret_cast<float2*>(prm.xlow)[xrow1 + af] = make_float2(s1.re, s1.im);
             }
             a0 = cmul(s0, w0);
             a1 = cmul(s1, w1);
         } else {
-            if (pos && live && prm.gw_re != nullptr) {
+            if (live && prm.gw_re != nullptr) {
                 const float2 x0 = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
                 const float2 x1 = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
                 const cf g0 = cmulc(s0, cf{x0.x, x0.y});   // G conj(X)
@@ -261,7 +270,7 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
                 atomicAdd(prm.gw_im + wrow0 + af, g0.im * prm.invT);
                 atomicAdd(prm.gw_re + wrow1 + af, g1.re * prm.invT);
                 atomicAdd(prm.gw_im + wrow1 + af, g1.im * prm.invT);
-                if (fs == 0) {
+                if (af == 0) {
                     atomicAdd(prm.gb + d0, s0.re);
                     atomicAdd(prm.gb + d0 + 1, s1.re);
                 }
@@ -269,14 +278,21 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
             a0 = cmulc(s0, w0);   // G conj(W)
             a1 = cmulc(s1, w1);
         }
-        cf c;
-        if (pos) {
-            c = cf{0.5f * (a0.re - a1.im), 0.5f * (a0.im + a1.re)};
-            if (j == 0 && ff1 == 0) c = cf{a0.re, a1.re};   // DC bin
-        } else {
-            c = cf{0.5f * (a0.re + a1.im), 0.5f * (a1.re - a0.im)};
+        const float h = 0.5f * prm.invT;
+        cf c = cf{h * (a0.re - a1.im), h * (a0.im + a1.re)};
+        if (af == 0) c = cf{a0.re * prm.invT, a1.re * prm.invT};   // DC bin
+        acc[j] = c;
+        cneg[j] = cf{h * (a0.re + a1.im), h * (a1.re - a0.im)};
+    }
+#pragma unroll
+    for (int jn = KJ; jn < NJ; ++jn) {
+        float cre = __shfl_sync(0xffffffffu, cneg[NJ - 1 - jn].re, src_lane);
+        float cim = __shfl_sync(0xffffffffu, cneg[NJ - 1 - jn].im, src_lane);
+        if (ff1 == 0) {   // mirror of -NR (NJ - jn) is the own bin j = NJ - jn (j = KJ is outside the band: zero)
+            cre = (NJ - jn < KJ) ? cneg[(NJ - jn) % KJ].re : 0.f;
+            cim = (NJ - jn < KJ) ? cneg[(NJ - jn) % KJ].im : 0.f;
         }
-        acc[j] = cf{c.re * prm.invT, c.im * prm.invT};
+        acc[jn] = cf{cre, cim};
     }
 }
 
@@ -350,6 +366,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
         cf acc[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[j] = cf{0.f, 0.f};
+        if constexpr (BWD) prefetch_xlow_l2<NR, KJ>(prm, b, dt * 2 * P + 2 * fp2, ff1);
 
         // ===================== analysis: R streamed passes, band accumulated in registers =====================
         for (int r = 0; r < R; ++r) {

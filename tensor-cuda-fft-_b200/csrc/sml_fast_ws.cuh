@@ -139,6 +139,10 @@ __global__ void __launch_bounds__(512, 1)
                 ++c;
                 ++L;
             }
+            // Role switch: from here on the T warps WAIT on yfull, a barrier they themselves arrived on during analysis.
+            // A warp two phases ahead of a slower sibling would see the stale parity and fall through, so all T warps
+            // meet here first (every analysis arrival has been made before any synthesis wait starts).
+            role_barrier(1, NTR);
             // ---------------- synthesis: Y -> iDFT over f1 -> +bias -> X -> TMA store ----------------
             const int td0 = dt * 2 * P + 2 * tp;
             cf bias2 = cf{0.f, 0.f};
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(512, 1)
             cf acc[NJ];
 #pragma unroll
             for (int j = 0; j < NJ; ++j) acc[j] = cf{0.f, 0.f};
+            if constexpr (BWD) prefetch_xlow_l2<NR, KJ>(prm, b, dt * 2 * P + 2 * fp2, ff1);
             // ---------------- analysis: Y -> DFT over m2 -> accumulate the band ----------------
             for (int r = 0; r < R; ++r) {
                 const float2 cjv = cj_load(r);
@@ -252,6 +257,9 @@ __global__ void __launch_bounds__(512, 1)
                 mbar_arrive(yfull + (c & 1u));
                 ++c;
             }
+            // Role switch (see the T role): the F warps arrived on yfull during synthesis and wait on it in the next
+            // tile's analysis; meet first so that no warp can be two phases ahead of the barrier.
+            role_barrier(2, NTR);
         }
     }
 }

@@ -1,0 +1,73 @@
+// sml_launch.cuh -- template definitions of the fused-kernel launchers (one explicit instantiation per sml_inst_*.cu).
+#pragma once
+
+#include <mutex>
+
+#include "sml_host.h"
+#include "sml_fast_ws.cuh"
+
+namespace sml_host {
+
+#define SML_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e));    \
+    } while (0)
+
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD>
+int launch_fast_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
+                     cudaStream_t stream) {
+    using C = sml::FastCfg<NR, P, IO>;
+    auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD>;
+    static std::once_flag once;   // one per instantiation
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    });
+    if (attr_err != cudaSuccess) return fail("cudaFuncSetAttribute(smem=%zu) failed: %s", C::SMEM_BYTES, cudaGetErrorString(attr_err));
+    kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map_in, map_out, prm);
+    count_launch();
+    SML_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KJ, typename IO, bool BWD>
+int launch_ws_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
+                   cudaStream_t stream) {
+    using C = sml::WsCfg<IO>;
+    auto kern = sml::sml_ws_kernel<KJ, IO, BWD>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    });
+    if (attr_err != cudaSuccess) return fail("cudaFuncSetAttribute(smem=%zu) failed: %s", C::SMEM_BYTES, cudaGetErrorString(attr_err));
+    kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map_in, map_out, prm);
+    count_launch();
+    SML_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename IO, bool BWD>
+int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm,
+                int grid, cudaStream_t stream) {
+    if (p.ws) {
+        if (p.KJ == 8) return launch_ws_inst<8, IO, BWD>(map_in, map_out, prm, grid, stream);
+        if (p.KJ == 12) return launch_ws_inst<12, IO, BWD>(map_in, map_out, prm, grid, stream);
+        return launch_ws_inst<16, IO, BWD>(map_in, map_out, prm, grid, stream);
+    }
+#define SML_CASE(NR_, KJ_, P_, MINB_) \
+    if (p.NR == NR_ && p.KJ == KJ_ && p.P == P_ && p.ctas_per_sm == MINB_) return launch_fast_inst<NR_, KJ_, P_, MINB_, IO, BWD>(map_in, map_out, prm, grid, stream);
+    SML_CASE(32, 8, 4, 3)
+    SML_CASE(32, 12, 4, 3)
+    SML_CASE(32, 16, 4, 2)
+    SML_CASE(32, 12, 4, 2)
+    SML_CASE(16, 4, 8, 3)
+    SML_CASE(16, 8, 8, 3)
+    SML_CASE(8, 4, 32, 2)
+#undef SML_CASE
+    return fail("internal: no fast kernel for NR=%d KJ=%d P=%d", p.NR, p.KJ, p.P);
+}
+
+
+}   // namespace sml_host

@@ -99,6 +99,40 @@ def spectral_mix(x: torch.Tensor, weight_real: torch.Tensor, weight_imag: torch.
     return _SpectralMixFn.apply(x, weight_real, weight_imag, bias)
 
 
+def spectral_mix_fwd_bwd_host(x: torch.Tensor, g: torch.Tensor, weight_real: torch.Tensor, weight_imag: torch.Tensor,
+                              bias: Optional[torch.Tensor] = None, chunk_batch: int = 0, out=None, device=None,
+                              filter_grads: bool = True):
+    """Forward + backward of the layer over HOST tensors through ``sml_fwd_bwd_host`` (include/spectral_mix_b200.h).
+
+    ``x`` and ``g`` are CPU tensors (B, T, D), fp32 or bf16 -- pinned memory lets the chunked host->device copies,
+    the kernels and the device->host copies overlap.  Returns CPU tensors ``(y, gx, gw_re, gw_im, gb)`` (the last
+    three are None with ``filter_grads=False``); ``out=(y, gx)`` reuses caller-provided (pinned) output buffers.
+    Same math as ``SpectralMixingLayer.forward`` + autograd backward (spectral_layers.py:88-116 of the reference)."""
+    if x.is_cuda or g.is_cuda:
+        raise RuntimeError("spectral_mix_fwd_bwd_host takes CPU tensors; use SpectralMixingLayer for device tensors")
+    if x.dtype not in _IO_DTYPES or g.dtype != x.dtype or x.shape != g.shape or x.dim() != 3:
+        raise RuntimeError(f"expected matching (B, T, D) fp32/bf16 tensors, got {tuple(x.shape)} {x.dtype} / {tuple(g.shape)} {g.dtype}")
+    B, T, D = x.shape
+    Fn = weight_real.shape[1]
+    x, g = x.contiguous(), g.contiguous()
+    wr = weight_real.detach().float().contiguous().cpu()
+    wi = weight_imag.detach().float().contiguous().cpu()
+    bs = None if bias is None else bias.detach().float().contiguous().cpu()
+    if out is None:
+        y = torch.empty_like(x, pin_memory=x.is_pinned())
+        gx = torch.empty_like(x, pin_memory=x.is_pinned())
+    else:
+        y, gx = out
+    gwr = gwi = gb = None
+    if filter_grads:
+        gwr, gwi, gb = torch.empty(D, Fn), torch.empty(D, Fn), torch.empty(D)
+    lib = _native.lib()
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        _native.check(lib.sml_fwd_bwd_host(_ptr(x), _ptr(g), _ptr(wr), _ptr(wi), _ptr(bs), _ptr(y), _ptr(gx), _ptr(gwr),
+                                           _ptr(gwi), _ptr(gb), B, T, D, Fn, _IO_DTYPES[x.dtype], int(chunk_batch)))
+    return y, gx, gwr, gwi, gb
+
+
 class SpectralMixingLayer(nn.Module):
     """Drop-in for ``fft_tensor.spectral_layers.SpectralMixingLayer`` (spectral_layers.py:19-132).
 

@@ -38,4 +38,18 @@ for (B, T, D) in shapes:
     for name, a, b in zip(("y", "gx", "gw_re", "gw_im", "gb"), res["0"], res["1"]):
         err = ((a - b).norm() / b.norm()).item()
         print(f"   {name}: rel-L2(ws1 vs ws0) = {err:.3e}")
+        if err > 1e-5 and name in ("y", "gx"):
+            # localise: which (b, 16-channel tile) and which row residue r = t mod R differ
+            R = max(T // 1024, 1)
+            d = (a - b).float().view(B, T // R, R, D // 16, 16)
+            per_tile = d.pow(2).sum(dim=(1, 2, 4)).sqrt()          # (B, ntd)
+            bad = (per_tile > 1e-3 * b.float().norm() / (B * D / 16) ** 0.5).nonzero().tolist()
+            print(f"      bad tiles (b, dt): {bad[:40]} ... total {len(bad)} of {B * D // 16}")
+            for (bb, dt) in bad[:4]:
+                e = d[bb, :, :, dt, :]                              # (T/R, R, 16)
+                print(f"      tile b={bb} dt={dt} linear={bb * (D // 16) + dt}: err by r = {e.pow(2).sum(dim=(0, 2)).sqrt().tolist()},"
+                      f" by channel = {[round(v, 3) for v in e.pow(2).sum(dim=(0, 1)).sqrt().tolist()]}")
+                m = e.pow(2).sum(dim=(1, 2)).sqrt()                 # by m (row within pass)
+                nz = (m > 1e-4).nonzero().flatten()
+                print(f"         rows m with error: count {nz.numel()} first {nz[:8].tolist()} last {nz[-8:].tolist()}")
 print("ws_debug done")
