@@ -44,8 +44,8 @@ def _fft_backend():
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=CFG["B"], help="per-GPU batch")
@@ -135,7 +135,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.002)
 
     def start(self):
         if self.ok:
@@ -270,7 +270,7 @@ def run_ours(args):
         ts = [a.elapsed_time(b) for a, b in evs]
         return sum(ts) / len(ts), min(ts)
 
-    nk = max(args.steps, 10)
+    nk = min(max(args.steps, 10), 100)
     fwd_ms, fwd_min = time_kernel(fwd, nk)
     bwd_ms, bwd_min = time_kernel(bwd, nk)
     peak, peak_src = load_peaks()
@@ -285,7 +285,7 @@ def run_ours(args):
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
 
     roofline = roof(bytes_bwd, bwd_ms)
-    roofline.update({"kernel": "sml_fast_kernel<BWD> (fused analysis + Wirtinger filter-grad + synthesis)" if plan["path"] == "fast" else "generic kernels",
+    roofline.update({"kernel": "sml_backward = sml_fast_kernel<BWD> (fused analysis + Wirtinger filter-grad terms + synthesis) + filtergrad_reduce_kernel" if plan["path"] == "fast" else "generic kernels",
                      "launch_ms": bwd_ms, "launch_ms_min": bwd_min, "algorithmic_bytes": bytes_bwd, "peak_source": peak_src})
     roofline_fwd = roof(bytes_fwd, fwd_ms)
     roofline_fwd.update({"kernel": "sml_fast_kernel<FWD>", "launch_ms": fwd_ms, "launch_ms_min": fwd_min, "algorithmic_bytes": bytes_fwd})

@@ -43,7 +43,7 @@ int sml_plan(int B, int T, int D, int F, int io_dtype, int* path, int* M, int* R
 /* Bytes of the saved low-band spectrum X_low = fft(x)[:, :k, :] in library layout (B, D, k) complex64. */
 size_t sml_xlow_bytes(int B, int T, int D, int F);
 
-/* Scratch bytes sml_backward needs (0 on the fast path). */
+/* Scratch bytes sml_backward needs (fast path: only when filter gradients are requested). */
 size_t sml_workspace_bytes(int B, int T, int D, int F, int io_dtype);
 
 /* Forward.  Replaces SpectralMixingLayer.forward steps 1-4, spectral_layers.py:88-116:
@@ -59,7 +59,8 @@ int sml_forward(const void* x, const float* w_re, const float* w_im, const float
  *   gW    = (1/T) sum_b fft(g)[b,:k,:] * conj(X_low[b])  -> gw_re = Re, gw_im = Im, columns >= k zero
  *   gb[d] = sum_{b,t} g[b,t,d]
  * gw_re/gw_im/gb are OVERWRITTEN (not accumulated).  Pass gw_re = gw_im = gb = NULL (and xlow = NULL) to get
- * gx only.  workspace: sml_workspace_bytes() bytes (may be NULL when that is 0). */
+ * gx only.  workspace: sml_workspace_bytes() bytes (on the fast path it may be NULL when no filter gradient is
+ * requested).  The batch reduction of gW and gb is a deterministic two-phase sum (no atomics). */
 int sml_backward(const void* g, const void* xlow, const float* w_re, const float* w_im, void* gx,
                  float* gw_re, float* gw_im, float* gb, void* workspace, size_t workspace_bytes, int B, int T,
                  int D, int F, int io_dtype, void* stream);

@@ -257,23 +257,19 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
     const float invT = 1.0f / (float)T;
     const bool aligned = ((uintptr_t)g % 16 == 0) && ((uintptr_t)gx % 16 == 0);
     if (p.path == SML_PATH_FAST && aligned) {
-        if (want_grads) {
-            const size_t nW = (size_t)D * F;
-            if (gw_im == gw_re + nW && gb == gw_im + nW) {   // one flat [gw_re | gw_im | gb] buffer (the host module's layout)
-                SML_CUDA(cudaMemsetAsync(gw_re, 0, sizeof(float) * (2 * nW + (size_t)D), stream));
-            } else {
-                SML_CUDA(cudaMemsetAsync(gw_re, 0, sizeof(float) * nW, stream));
-                SML_CUDA(cudaMemsetAsync(gw_im, 0, sizeof(float) * nW, stream));
-                SML_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)D, stream));
-            }
-        }
+        const size_t part_bytes = sizeof(sml::cf) * (size_t)B * D * (size_t)p.k;
+        const size_t need_ws = part_bytes + sizeof(float) * (size_t)B * D;
+        if (want_grads && (ws == nullptr || ws_bytes < need_ws))
+            return fail("workspace too small: need %zu bytes (sml_workspace_bytes), got %zu", need_ws, ws_bytes);
         CUtensorMap map, map_out;
         if (encode_act_map(&map, g, B, T, D, io_dtype, p)) return 1;
         if (encode_act_map(&map_out, gx, B, T, D, io_dtype, p)) return 1;
         sml::FastParams prm{};
         prm.out = gx; prm.w_re = w_re; prm.w_im = w_im; prm.bias = nullptr;
         prm.xlow = reinterpret_cast<sml::cf*>(const_cast<void*>(xlow));
-        prm.gw_re = gw_re; prm.gw_im = gw_im; prm.gb = gb;
+        prm.gw_re = gw_re;
+        prm.gpart = want_grads ? reinterpret_cast<sml::cf*>(ws) : nullptr;
+        prm.gbpart = want_grads ? reinterpret_cast<float*>(static_cast<char*>(ws) + part_bytes) : nullptr;
         prm.gtab = gtab;
         prm.B = B; prm.T = T; prm.D = D; prm.F = F; prm.k = p.k; prm.R = p.R;
         prm.ntd = (D + 2 * p.P - 1) / (2 * p.P);
@@ -282,7 +278,15 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         prm.dbg = debug_record();
         const int slots = st->sm_count * p.ctas_per_sm;
         const int grid = prm.ntiles < slots ? prm.ntiles : slots;
-        return launch_fast<IO, true>(p, map, map_out, prm, grid, stream);
+        if (launch_fast<IO, true>(p, map, map_out, prm, grid, stream)) return 1;
+        if (want_grads) {
+            const long long n = (long long)D * F;
+            sml::filtergrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+                reinterpret_cast<const float2*>(prm.gpart), prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k);
+            count_launch();
+            SML_CUDA(cudaGetLastError());
+        }
+        return 0;
     }
     // generic path: G into workspace, then synthesis with conj(W) and the batch reduction
     const size_t need = sizeof(sml::cf) * (size_t)B * D * (size_t)p.k;
@@ -502,7 +506,9 @@ size_t sml_xlow_bytes(int B, int T, int D, int F) {
 
 size_t sml_workspace_bytes(int B, int T, int D, int F, int io_dtype) {
     const Plan p = make_plan(T, D, F, io_dtype);
-    if (p.path == SML_PATH_FAST) return 0;
+    // fast path: per-batch-element filter-gradient terms (B,D,k) complex64 + bias-gradient terms (B,D) fp32;
+    // generic path: the low-band spectrum of g.  (Not needed when no filter gradient is requested on the fast path.)
+    if (p.path == SML_PATH_FAST) return sml_xlow_bytes(B, T, D, F) + sizeof(float) * (size_t)B * D;
     return sml_xlow_bytes(B, T, D, F);
 }
 

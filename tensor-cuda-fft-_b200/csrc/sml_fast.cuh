@@ -43,9 +43,9 @@ struct FastParams {
     const float* w_im;     // (D,F)
     const float* bias;     // (D,) or null            (FWD)
     cf* xlow;              // (B,D,k) complex64: written by FWD (nullable) / read by BWD (nullable)
-    float* gw_re;          // (D,F) zero-initialised, accumulated with atomics (BWD, nullable)
-    float* gw_im;
-    float* gb;             // (D,)
+    float* gw_re;          // (D,F): written by the reduction kernel that follows BWD; here only "filter grads wanted" (nullable)
+    cf* gpart;             // (B,D,k) per-batch-element filter-gradient terms (1/T) G conj(X_low), written by BWD
+    float* gbpart;         // (B,D)   per-batch-element bias-gradient terms Re G_0 = sum_t g
     const cf* gtab;        // W_T^n = exp(-2 pi i n / T), n < T
     int B, T, D, F, k, R;  // R = T / M passes
     int ntd;               // channel tiles = ceil(D / 2P)
@@ -221,37 +221,58 @@ __device__ __forceinline__ void prefetch_xlow_l2(const FastParams& prm, int b, i
 // mid phase (freq-side threads): acc holds the two-sided band Z of z = x_d + i x_{d+1}; on return it holds the band
 // C whose inverse transform is y_d + i y_{d+1}.  Hermitian split through warp shuffles (the partner bin -f lives in
 // lane NR - f1 of the same warp), complex filter (reference spectral_layers.py:101-105), and for BWD the Wirtinger
-// filter gradient G conj(X) (reference wirtinger_ops.py:77-80) reduced over the batch with fp32 atomics.
+// filter gradient terms G conj(X) (reference wirtinger_ops.py:77-80), one per batch element (summed by
+// filtergrad_reduce_kernel).
 // ------------------------------------------------------------------------------------------------
 template <int NR, int KJ, bool BWD>
 __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const FastParams& prm, int b, int d0, int ff1, int lane) {
     constexpr int NJ = 2 * KJ;
     const int D = prm.D;
     const bool pvalid = d0 < D;
+    const bool grads = BWD && prm.gw_re != nullptr;
     // the bin -fs of (ff1, j) lives in lane NR - ff1 of the same warp at index NJ - 1 - j (ff1 = 0: own index NJ - j)
     const int src_lane = (lane & ~(NR - 1)) | ((NR - ff1) & (NR - 1));
     const size_t wrow0 = (size_t)d0 * prm.F, wrow1 = wrow0 + prm.F;
     const size_t xrow0 = ((size_t)b * D + d0) * prm.k, xrow1 = xrow0 + prm.k;
-    cf cneg[KJ];   // filtered, re-packed value for the mirror bin -fs (handed back to its owner below)
+    // 1. issue every global load of this tile's mid phase up front (filter rows; BWD: saved X_low rows) so that their
+    //    latencies overlap -- the transform registers are dead here, so the values fit
+    float wv[KJ][4];
+    float2 xv[KJ][2];
 #pragma unroll
     for (int j = 0; j < KJ; ++j) {
-        const int af = ff1 + NR * j;   // fs >= 0: each thread filters its KJ non-negative bins and serves the mirrors
+        const int af = ff1 + NR * j;
+        const bool live = pvalid && af < prm.k;
+        wv[j][0] = wv[j][1] = wv[j][2] = wv[j][3] = 0.f;
+        xv[j][0] = xv[j][1] = make_float2(0.f, 0.f);
+        if (live) {
+            wv[j][0] = __ldg(prm.w_re + wrow0 + af);
+            wv[j][1] = __ldg(prm.w_im + wrow0 + af);
+            wv[j][2] = __ldg(prm.w_re + wrow1 + af);
+            wv[j][3] = __ldg(prm.w_im + wrow1 + af);
+            if (grads) {
+                xv[j][0] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
+                xv[j][1] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
+            }
+        }
+    }
+    // 2. each thread filters its KJ non-negative bins and serves the mirror bins of its partner lane
+    cf self_mirror = acc[0];   // ff1 == 0: the mirror of bin NR*j is the own bin at index NJ - j (DC mirrors itself)
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+        const int af = ff1 + NR * j;   // fs >= 0
         const bool live = pvalid && af < prm.k;
         float mre = __shfl_sync(0xffffffffu, acc[NJ - 1 - j].re, src_lane);
         float mim = __shfl_sync(0xffffffffu, acc[NJ - 1 - j].im, src_lane);
         if (ff1 == 0) {
-            mre = acc[(NJ - j) % NJ].re;
-            mim = acc[(NJ - j) % NJ].im;
+            mre = self_mirror.re;
+            mim = self_mirror.im;
         }
+        self_mirror = acc[NJ - 1 - j];   // = acc[NJ - (j + 1)], read before this iteration overwrites it
         const cf zp = acc[j], zm = cf{mre, mim};
         // Hermitian split: spectra of the two real channels at +af
         const cf s0 = cf{0.5f * (zp.re + zm.re), 0.5f * (zp.im - zm.im)};
         const cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
-        cf w0 = cf{0.f, 0.f}, w1 = cf{0.f, 0.f};
-        if (live) {
-            w0 = cf{__ldg(prm.w_re + wrow0 + af), __ldg(prm.w_im + wrow0 + af)};
-            w1 = cf{__ldg(prm.w_re + wrow1 + af), __ldg(prm.w_im + wrow1 + af)};
-        }
+        const cf w0 = cf{wv[j][0], wv[j][1]}, w1 = cf{wv[j][2], wv[j][3]};
         cf a0, a1;
         if constexpr (!BWD) {
             if (live && prm.xlow != nullptr) {
@@ -261,18 +282,16 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
             a0 = cmul(s0, w0);
             a1 = cmul(s1, w1);
         } else {
-            if (live && prm.gw_re != nullptr) {
-                const float2 x0 = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
-                const float2 x1 = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
-                const cf g0 = cmulc(s0, cf{x0.x, x0.y});   // G conj(X)
-                const cf g1 = cmulc(s1, cf{x1.x, x1.y});
-                atomicAdd(prm.gw_re + wrow0 + af, g0.re * prm.invT);
-                atomicAdd(prm.gw_im + wrow0 + af, g0.im * prm.invT);
-                atomicAdd(prm.gw_re + wrow1 + af, g1.re * prm.invT);
-                atomicAdd(prm.gw_im + wrow1 + af, g1.im * prm.invT);
+            if (live && grads) {
+                const cf g0 = cmulc(s0, cf{xv[j][0].x, xv[j][0].y});   // G conj(X)
+                const cf g1 = cmulc(s1, cf{xv[j][1].x, xv[j][1].y});
+                // per-batch-element terms; summed over the batch by filtergrad_reduce_kernel (deterministic, and no
+                // fp32 atomics, which serialise in the LSU at ~1.3 cycles per lane)
+                reinterpret_cast<float2*>(prm.gpart)[xrow0 + af] = make_float2(g0.re * prm.invT, g0.im * prm.invT);
+                reinterpret_cast<float2*>(prm.gpart)[xrow1 + af] = make_float2(g1.re * prm.invT, g1.im * prm.invT);
                 if (af == 0) {
-                    atomicAdd(prm.gb + d0, s0.re);
-                    atomicAdd(prm.gb + d0 + 1, s1.re);
+                    prm.gbpart[(size_t)b * D + d0] = s0.re;
+                    prm.gbpart[(size_t)b * D + d0 + 1] = s1.re;
                 }
             }
             a0 = cmulc(s0, w0);   // G conj(W)
@@ -282,17 +301,17 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
         cf c = cf{h * (a0.re - a1.im), h * (a0.im + a1.re)};
         if (af == 0) c = cf{a0.re * prm.invT, a1.re * prm.invT};   // DC bin
         acc[j] = c;
-        cneg[j] = cf{h * (a0.re + a1.im), h * (a1.re - a0.im)};
+        // hand the value for the mirror bin -fs to its owner (the partner does the same for this thread)
+        const cf cn = cf{h * (a0.re + a1.im), h * (a1.re - a0.im)};
+        acc[NJ - 1 - j].re = __shfl_sync(0xffffffffu, cn.re, src_lane);
+        acc[NJ - 1 - j].im = __shfl_sync(0xffffffffu, cn.im, src_lane);
     }
+    // ff1 == 0 lanes received their own values one index too low (bin -NR*j belongs at NJ - j); index KJ is the bin
+    // -NR*KJ, outside the band
+    if (ff1 == 0) {
 #pragma unroll
-    for (int jn = KJ; jn < NJ; ++jn) {
-        float cre = __shfl_sync(0xffffffffu, cneg[NJ - 1 - jn].re, src_lane);
-        float cim = __shfl_sync(0xffffffffu, cneg[NJ - 1 - jn].im, src_lane);
-        if (ff1 == 0) {   // mirror of -NR (NJ - jn) is the own bin j = NJ - jn (j = KJ is outside the band: zero)
-            cre = (NJ - jn < KJ) ? cneg[(NJ - jn) % KJ].re : 0.f;
-            cim = (NJ - jn < KJ) ? cneg[(NJ - jn) % KJ].im : 0.f;
-        }
-        acc[jn] = cf{cre, cim};
+        for (int idx = NJ - 1; idx > KJ; --idx) acc[idx] = acc[idx - 1];
+        acc[KJ] = cf{0.f, 0.f};
     }
 }
 
@@ -487,6 +506,34 @@ __global__ void __launch_bounds__(NR* P, MINB)
         }
     }
     if (tid == 0) tma_store_wait_all();
+}
+
+// batch reduction of the filter / bias gradient terms written by the BWD kernel (wirtinger_ops.py:77-80: sum over dim 0).
+// One thread per (d, f < F); also zero-fills the columns f >= k, so no memset is needed.  Deterministic.
+static __global__ void filtergrad_reduce_kernel(const float2* __restrict__ gpart, const float* __restrict__ gbpart,
+                                                float* __restrict__ gw_re, float* __restrict__ gw_im,
+                                                float* __restrict__ gb, int B, int D, int F, int k) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)D * F) return;
+    const int d = (int)(idx / F), f = (int)(idx - (long long)d * F);
+    float sr = 0.f, si = 0.f;
+    if (f < k) {
+        const float2* p = gpart + (size_t)d * k + f;
+        const size_t stride = (size_t)D * k;
+#pragma unroll 4
+        for (int b = 0; b < B; ++b) {
+            const float2 v = __ldg(p + (size_t)b * stride);
+            sr += v.x;
+            si += v.y;
+        }
+    }
+    gw_re[idx] = sr;
+    gw_im[idx] = si;
+    if (f == 0) {
+        float sb = 0.f;
+        for (int b = 0; b < B; ++b) sb += __ldg(gbpart + (size_t)b * D + d);
+        gb[d] = sb;
+    }
 }
 
 }   // namespace sml

@@ -59,6 +59,7 @@ class _SpectralMixFn(torch.autograd.Function):
         ctx.save_for_backward(wr, wi, xlow if need_filter_grad else None)
         ctx.shape = (B, T, D, Fn, io)
         ctx.has_bias = bias is not None
+        ctx.fast_path = plan["path"] == "fast"
         ctx.param_dtypes = (w_re.dtype, w_im.dtype, None if bias is None else bias.dtype)
         return y
 
@@ -80,7 +81,8 @@ class _SpectralMixFn(torch.autograd.Function):
             gwr = flat[: D * Fn].view(D, Fn)
             gwi = flat[D * Fn: 2 * D * Fn].view(D, Fn)
             gb = flat[2 * D * Fn:]
-        ws_bytes = lib.sml_workspace_bytes(B, T, D, Fn, io)
+        # fast path: scratch only for the filter-gradient terms; generic path: always (low-band spectrum of g)
+        ws_bytes = lib.sml_workspace_bytes(B, T, D, Fn, io) if (want or not ctx.fast_path) else 0
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gc.device) if ws_bytes else None
         with torch.cuda.device(gc.device):
             _native.check(lib.sml_backward(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gx), _ptr(gwr), _ptr(gwi),

@@ -48,7 +48,8 @@ def test_plan_selection(native):
 def test_buffer_sizes(native):
     lib = native.lib()
     assert lib.sml_xlow_bytes(16, 8192, 768, 384) == 16 * 768 * 384 * 8
-    assert lib.sml_workspace_bytes(16, 8192, 768, 384, 0) == 0
+    # fast path: per-batch-element filter-gradient terms (B,D,k) c64 + bias-gradient terms (B,D) f32
+    assert lib.sml_workspace_bytes(16, 8192, 768, 384, 0) == 16 * 768 * 384 * 8 + 16 * 768 * 4
     assert lib.sml_workspace_bytes(3, 100, 32, 16, 0) == 3 * 32 * 16 * 8
     assert lib.sml_xlow_bytes(2, 1, 4, 2) == 0
 

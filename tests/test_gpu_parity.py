@@ -209,8 +209,15 @@ def test_c_abi_direct(pkg, dev):
     n0 = lib.sml_launch_count()
     assert lib.sml_forward(xd.data_ptr(), wr.data_ptr(), wi.data_ptr(), bs.data_ptr(), y.data_ptr(), xlow.data_ptr(),
                            B, T, D, F, 0, s) == 0, lib.sml_last_error()
+    ws_bytes = lib.sml_workspace_bytes(B, T, D, F, 0)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     assert lib.sml_backward(gd.data_ptr(), xlow.data_ptr(), wr.data_ptr(), wi.data_ptr(), gx.data_ptr(),
-                            gwr.data_ptr(), gwi.data_ptr(), gb.data_ptr(), None, 0, B, T, D, F, 0, s) == 0, lib.sml_last_error()
+                            gwr.data_ptr(), gwi.data_ptr(), gb.data_ptr(), ws.data_ptr(), ws_bytes, B, T, D, F, 0, s) == 0, lib.sml_last_error()
+    # filter gradients without the workspace are refused, gx-only needs none
+    assert lib.sml_backward(gd.data_ptr(), xlow.data_ptr(), wr.data_ptr(), wi.data_ptr(), gx.data_ptr(),
+                            gwr.data_ptr(), gwi.data_ptr(), gb.data_ptr(), None, 0, B, T, D, F, 0, s) != 0
+    assert lib.sml_backward(gd.data_ptr(), None, wr.data_ptr(), wi.data_ptr(), gx.data_ptr(),
+                            None, None, None, None, 0, B, T, D, F, 0, s) == 0, lib.sml_last_error()
     torch.cuda.synchronize()
     assert lib.sml_launch_count() - n0 >= 2
     for name, a in zip(NAMES, (y, gx, gwr, gwi, gb)):      # outputs are overwritten, not accumulated

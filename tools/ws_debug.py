@@ -23,11 +23,12 @@ for (B, T, D) in shapes:
         xlow = torch.empty(lib.sml_xlow_bytes(B, T, D, Fn), dtype=torch.uint8, device=dev)
         gwr, gwi, gb = torch.empty(D, Fn, device=dev), torch.empty(D, Fn, device=dev), torch.empty(D, device=dev)
         st = torch.cuda.current_stream().cuda_stream
+        wsb = torch.empty(max(lib.sml_workspace_bytes(B, T, D, Fn, 0), 1), dtype=torch.uint8, device=dev)
         try:
             _native.check(lib.sml_forward(x.data_ptr(), wr.data_ptr(), wi.data_ptr(), bs.data_ptr(), y.data_ptr(), xlow.data_ptr(), B, T, D, Fn, 0, st))
             torch.cuda.synchronize()
             print(f"{(B, T, D)} ws={ws} fwd ok", flush=True)
-            _native.check(lib.sml_backward(g.data_ptr(), xlow.data_ptr(), wr.data_ptr(), wi.data_ptr(), gx.data_ptr(), gwr.data_ptr(), gwi.data_ptr(), gb.data_ptr(), None, 0, B, T, D, Fn, 0, st))
+            _native.check(lib.sml_backward(g.data_ptr(), xlow.data_ptr(), wr.data_ptr(), wi.data_ptr(), gx.data_ptr(), gwr.data_ptr(), gwi.data_ptr(), gb.data_ptr(), wsb.data_ptr(), wsb.numel(), B, T, D, Fn, 0, st))
             torch.cuda.synchronize()
             print(f"{(B, T, D)} ws={ws} bwd ok", flush=True)
         except Exception as e:
