@@ -284,11 +284,19 @@ def run_ours(args):
         ach = nbytes / (ms * 1e-3) / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
 
+    traffic = {}
+    try:    # measured DRAM bytes per launch from the committed ncu capture (only for the exact profiled configuration)
+        if (B, T, D, args.dtype) == (16, 8192, 768, "f32"):
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["cfg2_f32"]
+    except Exception:
+        traffic = {}
     roofline = roof(bytes_bwd, bwd_ms)
     roofline.update({"kernel": "sml_backward = sml_fast_kernel<BWD> (fused analysis + Wirtinger filter-grad terms + synthesis) + filtergrad_reduce_kernel" if plan["path"] == "fast" else "generic kernels",
-                     "launch_ms": bwd_ms, "launch_ms_min": bwd_min, "algorithmic_bytes": bytes_bwd, "peak_source": peak_src})
+                     "launch_ms": bwd_ms, "launch_ms_min": bwd_min, "algorithmic_bytes": bytes_bwd, "peak_source": peak_src,
+                     "traffic": traffic.get("sml_backward"), "traffic_source": "profiles/traffic.json (ncu --set full)" if traffic else None})
     roofline_fwd = roof(bytes_fwd, fwd_ms)
-    roofline_fwd.update({"kernel": "sml_fast_kernel<FWD>", "launch_ms": fwd_ms, "launch_ms_min": fwd_min, "algorithmic_bytes": bytes_fwd})
+    roofline_fwd.update({"kernel": "sml_fast_kernel<FWD>", "launch_ms": fwd_ms, "launch_ms_min": fwd_min, "algorithmic_bytes": bytes_fwd,
+                         "traffic": traffic.get("sml_forward")})
     roofline_step = roof(bytes_step, ms_step)
     roofline_step.update({"note": "4-pass floor bytes / whole fwd+bwd step time (includes host launch gaps and, at N>1, the all-reduce)"})
 

@@ -38,6 +38,7 @@
 namespace sml {
 
 struct FastParams {
+    const void* in;        // x (FWD) or g (BWD): (B,T,D) IO -- used by the cp.async load path
     void* out;             // y (FWD) or gx (BWD): (B,T,D) IO
     const float* w_re;     // (D,F)
     const float* w_im;     // (D,F)
@@ -318,7 +319,10 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int NR, int KJ, int P, int MINB, typename IO, bool BWD>
+// CPA selects the load path: false = TMA tile loads issued by one thread; true = per-thread 16-byte cp.async.cg
+// (measured on B200, tools/microbench/ldst_stream.cu: with 32-byte rows a TMA-load + TMA-store stream of the cfg-2 tensor
+// takes 0.183 ms, cp.async loads + TMA stores 0.157 ms; with 16-byte rows (bf16, P = 4) TMA loads win, 0.115 vs 0.18 ms).
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, bool CPA>
 __global__ void __launch_bounds__(NR* P, MINB)
     sml_fast_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                     const FastParams prm) {
@@ -344,6 +348,34 @@ __global__ void __launch_bounds__(NR* P, MINB)
     const int my_ntiles = (prm.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_loads = my_ntiles * R;
 
+    // cp.async path: a warp's threads (p = tid % P, m2 = tid / P) read exactly the rows m with m % NR in
+    // [wm2, wm2 + 32 / P), all 2P channels -- so each warp owns its rows of X and refills them by itself, right after its
+    // own drain, with no CTA-wide synchronisation.  Every thread arrives on the mbarrier when its copies have landed.
+    auto issue_load_cpa = [&](int L) {   // all threads (warp-collective)
+        if (L >= total_loads) return;
+        constexpr int CPR = 2 * P * (int)sizeof(IO) / 16;        // 16-byte chunks per row
+        constexpr int RPW = 32 / P;                              // row residues owned by one warp
+        constexpr int NCH = NR * RPW * CPR;                      // chunks per warp and pass
+        static_assert(CPR >= 1 && NCH % 32 == 0, "cp.async load path needs rows of at least 16 bytes");
+        const int it = L / R, r = L - it * R;
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int b = tile / prm.ntd, dt = tile - b * prm.ntd;
+        const int lane = tid & 31, wm2 = (tid >> 5) * RPW;
+        const size_t row_bytes = (size_t)D * sizeof(IO);
+        const char* src0 = reinterpret_cast<const char*>(prm.in) + ((size_t)b * T + r) * row_bytes + (size_t)dt * 2 * P * sizeof(IO);
+        const int valid_bytes = (D - dt * 2 * P) * (int)sizeof(IO);   // channel-tile tail: chunks past D are zero-filled
+#pragma unroll
+        for (int i = 0; i < NCH / 32; ++i) {
+            const int q = lane + 32 * i;
+            const int part = q % CPR, j = (q / CPR) % RPW, m1 = q / (CPR * RPW);
+            const int row = NR * m1 + wm2 + j;
+            const bool ok = part * 16 < valid_bytes;
+            const char* src = src0 + (size_t)row * R * row_bytes + (ok ? part * 16 : 0);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                         ::"r"(smem_u32(xbuf + (size_t)row * 2 * P * sizeof(IO) + part * 16)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+    };
     auto issue_load = [&](int L) {   // thread 0 only.  load L = (tile L / R, pass L % R) -> X
         if (L >= total_loads) return;
         const int it = L / R, r = L - it * R;
@@ -368,12 +400,13 @@ __global__ void __launch_bounds__(NR* P, MINB)
     };
 
     if (tid == 0) {
-        mbar_init(mbar, 1);
+        mbar_init(mbar, CPA ? NT : 1);
         fence_mbar_init();
         *xdone = 0u;
     }
     __syncthreads();
-    if (tid == 0) issue_load(0);
+    if constexpr (CPA) issue_load_cpa(0);
+    else if (tid == 0) issue_load(0);
 
     int L = 0;      // loads consumed so far
     int slot = 0;   // cj slot of the current pass
@@ -407,7 +440,9 @@ __global__ void __launch_bounds__(NR* P, MINB)
             // last pass, so nothing is prefetched across the analysis/synthesis boundary)
             if (r + 1 < R) {
                 __syncwarp();
-                if ((tid & 31) == 0) {
+                if constexpr (CPA) {
+                    issue_load_cpa(L + 1);   // this warp's own rows: no other warp reads them
+                } else if ((tid & 31) == 0) {
                     __threadfence_block();
                     if ((atomicAdd(xdone, 1u) % (NT / 32)) == NT / 32 - 1) issue_load(L + 1);
                 }
@@ -500,7 +535,11 @@ __global__ void __launch_bounds__(NR* P, MINB)
             if (tid == 0) issue_store(b, dt, r);
             slot ^= 1;
         }
-        if (tid == 0) {
+        if constexpr (CPA) {
+            if (tid == 0) tma_store_wait_read();
+            __syncthreads();         // the last staging tile has left X
+            issue_load_cpa(L);       // pass 0 of the next tile
+        } else if (tid == 0) {
             tma_store_wait_read();
             issue_load(L);   // pass 0 of the next tile
         }

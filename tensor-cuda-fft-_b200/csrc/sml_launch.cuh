@@ -18,7 +18,11 @@ template <int NR, int KJ, int P, int MINB, typename IO, bool BWD>
 int launch_fast_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
                      cudaStream_t stream) {
     using C = sml::FastCfg<NR, P, IO>;
-    auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD>;
+    // In a copy-only stream cp.async loads beat TMA loads for rows of >= 32 bytes (tools/microbench/ldst_stream.cu), but
+    // measured in the real kernel (cfg-2 fp32): cp.async loads 0.227 ms vs TMA loads 0.198 ms per forward launch -- the
+    // per-thread copies compete with the exchange traffic for the LSU/shared-memory pipe, so TMA stays the load path.
+    constexpr bool CPA = false;
+    auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD, CPA>;
     static std::once_flag once;   // one per instantiation
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] {
