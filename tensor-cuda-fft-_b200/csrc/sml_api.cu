@@ -282,8 +282,8 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         const int grid = prm.ntiles < slots ? prm.ntiles : slots;
         if (launch_fast<IO, true>(p, map, map_out, prm, grid, stream)) return 1;
         if (want_grads) {
-            const long long n = (long long)D * F;
-            sml::filtergrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+            const long long n = (long long)D * ((F + 1) / 2);
+            sml::filtergrad_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(
                 reinterpret_cast<const float2*>(prm.gpart), prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k);
             count_launch();
             SML_CUDA(cudaGetLastError());

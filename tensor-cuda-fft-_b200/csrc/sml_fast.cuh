@@ -548,26 +548,38 @@ __global__ void __launch_bounds__(NR* P, MINB)
 }
 
 // batch reduction of the filter / bias gradient terms written by the BWD kernel (wirtinger_ops.py:77-80: sum over dim 0).
-// One thread per (d, f < F); also zero-fills the columns f >= k, so no memset is needed.  Deterministic.
+// One thread per (d, pair of bins f, f+1 < F) -- k is even on the fast path (k = min(F, T/2) with T a power of two and
+// 2k <= M, or k = F handled by the scalar tail); also zero-fills the columns f >= k, so no memset is needed.
+// Deterministic (fixed summation order over b).
 static __global__ void filtergrad_reduce_kernel(const float2* __restrict__ gpart, const float* __restrict__ gbpart,
                                                 float* __restrict__ gw_re, float* __restrict__ gw_im,
                                                 float* __restrict__ gb, int B, int D, int F, int k) {
+    const int F2 = (F + 1) / 2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)D * F) return;
-    const int d = (int)(idx / F), f = (int)(idx - (long long)d * F);
-    float sr = 0.f, si = 0.f;
-    if (f < k) {
-        const float2* p = gpart + (size_t)d * k + f;
-        const size_t stride = (size_t)D * k;
-#pragma unroll 4
+    if (idx >= (long long)D * F2) return;
+    const int d = (int)(idx / F2), f = 2 * (int)(idx - (long long)d * F2);
+    float sr0 = 0.f, si0 = 0.f, sr1 = 0.f, si1 = 0.f;
+    const size_t stride = (size_t)D * k;
+    const float2* p = gpart + (size_t)d * k + f;
+    if (f + 1 < k && ((((size_t)d * k + f) & 1) == 0) && (stride & 1) == 0) {   // both bins live and 16-byte aligned
+#pragma unroll 8
         for (int b = 0; b < B; ++b) {
-            const float2 v = __ldg(p + (size_t)b * stride);
-            sr += v.x;
-            si += v.y;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)b * stride));
+            sr0 += v.x; si0 += v.y; sr1 += v.z; si1 += v.w;
+        }
+    } else {
+        for (int b = 0; b < B; ++b) {
+            if (f < k) { const float2 v = __ldg(p + (size_t)b * stride); sr0 += v.x; si0 += v.y; }
+            if (f + 1 < k) { const float2 v = __ldg(p + 1 + (size_t)b * stride); sr1 += v.x; si1 += v.y; }
         }
     }
-    gw_re[idx] = sr;
-    gw_im[idx] = si;
+    const size_t o = (size_t)d * F + f;
+    gw_re[o] = sr0;
+    gw_im[o] = si0;
+    if (f + 1 < F) {
+        gw_re[o + 1] = sr1;
+        gw_im[o + 1] = si1;
+    }
     if (f == 0) {
         float sb = 0.f;
         for (int b = 0; b < B; ++b) sb += __ldg(gbpart + (size_t)b * D + d);

@@ -15,8 +15,10 @@
 //       analysis : Y[c&1] -> DFT_32 over m2 -> acc += twiddle * (live bins)               (consumer of Y)
 //       mid phase: Hermitian split, complex filter (+ X_low save / Wirtinger filter gradient)
 //       synthesis: acc -> iDFT_32 over f2 -> twiddle powers -> Y[c&1]                     (producer of Y)
-// Y is double buffered (full/empty mbarriers, 256 arrivals each), so T works on pass c+1 while F works on pass c.
-// Register budgets are rebalanced with setmaxnreg (T: 104, F: 152 registers per thread).
+// Buffers: X is double buffered (two TMA landing tiles, loads run two passes ahead; during synthesis one of them is the
+// store staging tile while the other already receives pass 0 of the next work item); the exchange tile Y is single
+// (full/empty mbarriers, 256 arrivals each): a role only holds it for the copy in or out, the butterflies of pass c+1 (T)
+// and pass c (F) still overlap.  Register budgets are rebalanced with setmaxnreg (T: 104, F: 152 registers per thread).
 #pragma once
 
 #include "sml_fast.cuh"
@@ -34,7 +36,7 @@ struct WsCfg {
     static constexpr uint32_t XBUF_BYTES = (LOAD_BYTES + 127u) & ~127u;
     static constexpr uint32_t YBUF_BYTES = ((uint32_t)NT_ROLE * XS * sizeof(cf) + 127u) & ~127u;
     static constexpr uint32_t CJ_BYTES = (uint32_t)P * NR * sizeof(cf);   // one private slot per F warp
-    static constexpr size_t SMEM_BYTES = (size_t)XBUF_BYTES + 2u * YBUF_BYTES + CJ_BYTES + 8 * sizeof(uint64_t);
+    static constexpr size_t SMEM_BYTES = 2u * (size_t)XBUF_BYTES + YBUF_BYTES + CJ_BYTES + 8 * sizeof(uint64_t);
     static constexpr int REGS_T = 104, REGS_F = 152;
 };
 
@@ -60,15 +62,15 @@ __global__ void __launch_bounds__(512, 1)
     static_assert(NJ <= NR, "band wider than the sub-transform");
 
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* const xbuf = smem;                                                        // landing / staging [M][2P]
-    cf* const ybuf0 = reinterpret_cast<cf*>(smem + C::XBUF_BYTES);                           // exchange [2][256][XS]
-    cf* const cjbuf = reinterpret_cast<cf*>(smem + C::XBUF_BYTES + 2u * C::YBUF_BYTES);      // [P][NR]
+    unsigned char* const xbuf0 = smem;                                                       // 2 x landing / staging [M][2P]
+    cf* const ybuf = reinterpret_cast<cf*>(smem + 2u * C::XBUF_BYTES);                       // exchange [256][XS]
+    cf* const cjbuf = reinterpret_cast<cf*>(smem + 2u * C::XBUF_BYTES + C::YBUF_BYTES);      // [P][NR]
     uint64_t* const bars = reinterpret_cast<uint64_t*>(cjbuf + P * NR);
-    uint64_t* const xfull = bars;            // TMA landed (tx)
-    uint64_t* const yfull = bars + 1;        // [2] producer role has written Y[b]
-    uint64_t* const yempty = bars + 3;       // [2] consumer role has drained Y[b]
-    unsigned int* const xdone = reinterpret_cast<unsigned int*>(bars + 5);   // T warps that have drained X
-    auto ybuf = [&](int i) -> cf* { return reinterpret_cast<cf*>(reinterpret_cast<unsigned char*>(ybuf0) + (size_t)i * C::YBUF_BYTES); };
+    uint64_t* const xfull = bars;            // [2] TMA landed (tx)
+    uint64_t* const yfull = bars + 2;        // producer role has written Y
+    uint64_t* const yempty = bars + 3;       // consumer role has drained Y
+    unsigned int* const xdone = reinterpret_cast<unsigned int*>(bars + 4);   // [2] T warps that have drained X[slot]
+    auto xbuf = [&](int slot) -> unsigned char* { return xbuf0 + (size_t)slot * C::XBUF_BYTES; };
 
     const int tid = threadIdx.x;
     const int R = prm.R, T = prm.T, D = prm.D;
@@ -77,11 +79,11 @@ __global__ void __launch_bounds__(512, 1)
 
     if (tid == 0) {
         mbar_init(xfull, 1);
+        mbar_init(xfull + 1, 1);
         mbar_init(yfull, NTR);
-        mbar_init(yfull + 1, NTR);
         mbar_init(yempty, NTR);
-        mbar_init(yempty + 1, NTR);
-        *xdone = 0u;
+        xdone[0] = 0u;
+        xdone[1] = 0u;
         fence_mbar_init();
     }
     __syncthreads();
@@ -93,18 +95,26 @@ __global__ void __launch_bounds__(512, 1)
         setmaxnreg_dec<C::REGS_T>();
         const int tp = tid % P, tm2 = tid / P;
         const int total_loads = my_ntiles * R;
-        auto issue_load = [&](int L) {   // one thread.  load L = (tile L / R, pass L % R) -> X
-            if (L >= total_loads) return;
-            const int it = L / R, r = L - it * R;
+        // load n = (tile n / R, pass n % R) -> X[n & 1]; completion on xfull[n & 1], phase (n >> 1).
+        // Order of issue: 0 and 1 up front; draining load L (not the last pass of its tile) frees its slot for L + 2;
+        // the slot of a tile's last load is the store staging tile during synthesis and is re-armed (load + 1 of the next
+        // tile) once the tile's last store has left it.
+        auto issue_load = [&](int n) {   // one thread
+            if (n >= total_loads) return;
+            const int it = n / R, r = n - it * R;
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int b = tile / prm.ntd, dt = tile - b * prm.ntd;
+            unsigned char* dst = xbuf(n & 1);
             fence_proxy_async();
-            mbar_expect_tx(xfull, C::LOAD_BYTES);
+            mbar_expect_tx(xfull + (n & 1), C::LOAD_BYTES);
 #pragma unroll
             for (int bx = 0; bx < C::NBOX; ++bx)
-                tma_load_4d(xbuf + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), &tmap_in, xfull, dt * 2 * P, r, bx * C::BOXROWS, b);
+                tma_load_4d(dst + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), &tmap_in, xfull + (n & 1), dt * 2 * P, r, bx * C::BOXROWS, b);
         };
-        if (tid == 0) issue_load(0);
+        if (tid == 0) {
+            issue_load(0);
+            issue_load(1);
+        }
         int L = 0;          // loads consumed
         unsigned int c = 0; // Y passes so far (analysis and synthesis alike)
         for (int it = 0; it < my_ntiles; ++it) {
@@ -113,29 +123,30 @@ __global__ void __launch_bounds__(512, 1)
             // ---------------- analysis: X -> DFT over m1 -> twiddle -> Y ----------------
             for (int r = 0; r < R; ++r) {
                 const float2 wb = __ldg(gtab + (R * tm2 + r));   // W_T^{R m2 + r}
-                mbar_wait(xfull, (uint32_t)L & 1u, prm.dbg, 10u, (uint32_t)L);
+                const int slot = L & 1;
+                mbar_wait(xfull + slot, ((uint32_t)L >> 1) & 1u, prm.dbg, 10u, (uint32_t)L);
                 cf v[NR];
                 {
-                    const IO* src = reinterpret_cast<const IO*>(xbuf) + tm2 * 2 * P + 2 * tp;
+                    const IO* src = reinterpret_cast<const IO*>(xbuf(slot)) + tm2 * 2 * P + 2 * tp;
 #pragma unroll
                     for (int m1 = 0; m1 < NR; ++m1) v[m1] = PairIO<IO>::load_s(src + m1 * NR * 2 * P);
                 }
-                if (r + 1 < R) {   // the last T warp to drain X re-arms it with the next pass
+                if (r + 1 < R) {   // the last T warp to drain X[slot] re-arms it two loads ahead
                     __syncwarp();
                     if ((tid & 31) == 0) {
                         __threadfence_block();
-                        if ((atomicAdd(xdone, 1u) % (NTR / 32)) == NTR / 32 - 1) issue_load(L + 1);
+                        if ((atomicAdd(xdone + slot, 1u) % (NTR / 32)) == NTR / 32 - 1) issue_load(L + 2);
                     }
                 }
                 Dft<NR, -1>::run(v);
                 apply_power_twiddles<NR, false, true>(v, cf{1.f, 0.f}, cf{wb.x, wb.y});
-                mbar_wait(yempty + (c & 1u), ((c >> 1) & 1u) ^ 1u, prm.dbg, 11u, c);
+                mbar_wait(yempty, (c & 1u) ^ 1u, prm.dbg, 11u, c);
                 {
-                    float4* xrow = reinterpret_cast<float4*>(ybuf(c & 1u) + tid * XS);
+                    float4* xrow = reinterpret_cast<float4*>(ybuf + tid * XS);
 #pragma unroll
                     for (int h = 0; h < NR / 2; ++h) xrow[h] = make_float4(v[2 * h].re, v[2 * h].im, v[2 * h + 1].re, v[2 * h + 1].im);
                 }
-                mbar_arrive(yfull + (c & 1u));
+                mbar_arrive(yfull);
                 ++c;
                 ++L;
             }
@@ -143,7 +154,8 @@ __global__ void __launch_bounds__(512, 1)
             // A warp two phases ahead of a slower sibling would see the stale parity and fall through, so all T warps
             // meet here first (every analysis arrival has been made before any synthesis wait starts).
             role_barrier(1, NTR);
-            // ---------------- synthesis: Y -> iDFT over f1 -> +bias -> X -> TMA store ----------------
+            // ---------------- synthesis: Y -> iDFT over f1 -> +bias -> staging tile -> TMA store ----------------
+            unsigned char* const stage = xbuf((L - 1) & 1);   // slot of the tile's last load (drained by every T warp)
             const int td0 = dt * 2 * P + 2 * tp;
             cf bias2 = cf{0.f, 0.f};
             if constexpr (!BWD) {
@@ -151,9 +163,9 @@ __global__ void __launch_bounds__(512, 1)
             }
             for (int r = 0; r < R; ++r) {
                 cf v[NR];
-                mbar_wait(yfull + (c & 1u), (c >> 1) & 1u, prm.dbg, 12u, c);
+                mbar_wait(yfull, c & 1u, prm.dbg, 12u, c);
                 {
-                    const float4* xrow = reinterpret_cast<const float4*>(ybuf(c & 1u) + tid * XS);
+                    const float4* xrow = reinterpret_cast<const float4*>(ybuf + tid * XS);
 #pragma unroll
                     for (int h = 0; h < NR / 2; ++h) {
                         const float4 q = xrow[h];
@@ -161,12 +173,12 @@ __global__ void __launch_bounds__(512, 1)
                         v[2 * h + 1] = cf{q.z, q.w};
                     }
                 }
-                mbar_arrive(yempty + (c & 1u));
+                mbar_arrive(yempty);
                 Dft<NR, +1>::run(v);
-                if (tid == 0 && r > 0) tma_store_wait_read();   // previous rows have left X
-                role_barrier(1, NTR);                           // X is free (and, at r == 0, drained by every T warp)
+                if (tid == 0 && r > 0) tma_store_wait_read();   // previous rows have left the staging tile
+                role_barrier(1, NTR);
                 {
-                    IO* dst = reinterpret_cast<IO*>(xbuf) + tm2 * 2 * P + 2 * tp;
+                    IO* dst = reinterpret_cast<IO*>(stage) + tm2 * 2 * P + 2 * tp;
 #pragma unroll
                     for (int m1 = 0; m1 < NR; ++m1) PairIO<IO>::store_s(dst + m1 * NR * 2 * P, cadd(v[m1], bias2));
                 }
@@ -175,14 +187,14 @@ __global__ void __launch_bounds__(512, 1)
                 if (tid == 0) {
 #pragma unroll
                     for (int bx = 0; bx < C::NBOX; ++bx)
-                        tma_store_4d(&tmap_out, xbuf + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), dt * 2 * P, r, bx * C::BOXROWS, b);
+                        tma_store_4d(&tmap_out, stage + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), dt * 2 * P, r, bx * C::BOXROWS, b);
                     tma_store_commit();
                 }
                 ++c;
             }
             if (tid == 0) {
                 tma_store_wait_read();
-                issue_load(L);   // pass 0 of the next tile
+                issue_load(L + 1);   // the staging slot's next load: pass 1 of the next tile (pass 0 is already in flight)
             }
         }
         if (tid == 0) tma_store_wait_all();
@@ -210,13 +222,13 @@ __global__ void __launch_bounds__(512, 1)
             for (int r = 0; r < R; ++r) {
                 const float2 cjv = cj_load(r);
                 cf v[NR];
-                mbar_wait(yfull + (c & 1u), (c >> 1) & 1u, prm.dbg, 20u, c);
+                mbar_wait(yfull, c & 1u, prm.dbg, 20u, c);
                 {
-                    const cf* xb = ybuf(c & 1u) + fp2 * XS + ff1;
+                    const cf* xb = ybuf + fp2 * XS + ff1;
 #pragma unroll
                     for (int m2 = 0; m2 < NR; ++m2) v[m2] = xb[m2 * P * XS];
                 }
-                mbar_arrive(yempty + (c & 1u));
+                mbar_arrive(yempty);
                 __syncwarp();
                 cjs[ff1] = cf{cjv.x, cjv.y};
                 __syncwarp();
@@ -248,13 +260,13 @@ __global__ void __launch_bounds__(512, 1)
                 }
                 Dft<NR, +1>::run(v);
                 apply_power_twiddles<NR, true, false>(v, cf{sr.x, sr.y}, cf{beta.x, beta.y});
-                mbar_wait(yempty + (c & 1u), ((c >> 1) & 1u) ^ 1u, prm.dbg, 21u, c);
+                mbar_wait(yempty, (c & 1u) ^ 1u, prm.dbg, 21u, c);
                 {
-                    cf* xb = ybuf(c & 1u) + fp2 * XS + ff1;
+                    cf* xb = ybuf + fp2 * XS + ff1;
 #pragma unroll
                     for (int m2 = 0; m2 < NR; ++m2) xb[m2 * P * XS] = v[m2];
                 }
-                mbar_arrive(yfull + (c & 1u));
+                mbar_arrive(yfull);
                 ++c;
             }
             // Role switch (see the T role): the F warps arrived on yfull during synthesis and wait on it in the next

@@ -14,7 +14,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, flat_layout=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -35,18 +35,28 @@ def _worker(rank, world, port, q):
     m.weight_real.grad = mine.sum(dim=(0, 1)).unsqueeze(1).repeat(1, 3)
     m.weight_imag.grad = 2 * m.weight_real.grad
     m.bias.grad = mine.sum(dim=(0, 1))
+    if flat_layout:     # the layout the fused backward hands out: three views of one [gw_re | gw_im | gb] buffer
+        flat = torch.cat([m.weight_real.grad.reshape(-1), m.weight_imag.grad.reshape(-1), m.bias.grad])
+        m.weight_real.grad, m.weight_imag.grad, m.bias.grad = flat[:12].view(4, 3), flat[12:24].view(4, 3), flat[24:]
+        ptr = flat.data_ptr()
     allreduce_filter_grads([m])
+    if flat_layout:     # reduced in place: no concatenation, no copy back
+        assert m.weight_real.grad.data_ptr() == ptr and m.bias.grad.data_ptr() == ptr + 24 * 4
     q.put((rank, mine.shape[0], m.weight_real.grad.clone(), m.weight_imag.grad.clone(), m.bias.grad.clone()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_filter_grad_allreduce():
+import pytest
+
+
+@pytest.mark.parametrize("flat_layout", [False, True])
+def test_sharded_filter_grad_allreduce(flat_layout):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, flat_layout)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])

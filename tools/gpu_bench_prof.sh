@@ -11,6 +11,6 @@ $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "ncu launches exit $?"
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"sml_fast|filtergrad" -s 9 -c 3 -o gpurun_out/prof_$TAG -f $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"sml_fast|sml_ws|filtergrad" -s 9 -c 3 -o gpurun_out/prof_$TAG -f $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "ncu full exit $?"; tail -n 3 gpurun_out/ncu_full_$TAG.log
 ls -la gpurun_out

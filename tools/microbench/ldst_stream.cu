@@ -29,8 +29,10 @@ __global__ void __launch_bounds__(128, 3)
     unsigned char* S = smem + M * ROWB;         // staging (TMA store path only)
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * M * ROWB);
     const int tid = threadIdx.x, tp = tid % 4, tm2 = tid / 4;
+    uint64_t pol = 0;
+    if (LD == 4) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(LD == 0 ? 1 : 128));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"((LD == 0 || LD == 4) ? 1 : 128));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     __syncthreads();
@@ -47,13 +49,18 @@ __global__ void __launch_bounds__(128, 3)
         if (L >= total) return;
         int b, dt, r;
         coords(L, b, dt, r);
-        if (LD == 0) {
+        if (LD == 0 || LD == 4) {
             if (tid == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(M * ROWB) : "memory");
-                for (int bx = 0; bx < M / BOX; ++bx)
-                    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                                 ::"r"(s32(X + bx * BOX * ROWB)), "l"((uint64_t)&tin), "r"(s32(bar)), "r"(dt * 8), "r"(r), "r"(bx * BOX), "r"(b) : "memory");
+                for (int bx = 0; bx < M / BOX; ++bx) {
+                    if (LD == 4)
+                        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                                     ::"r"(s32(X + bx * BOX * ROWB)), "l"((uint64_t)&tin), "r"(s32(bar)), "r"(dt * 8), "r"(r), "r"(bx * BOX), "r"(b), "l"(pol) : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                                     ::"r"(s32(X + bx * BOX * ROWB)), "l"((uint64_t)&tin), "r"(s32(bar)), "r"(dt * 8), "r"(r), "r"(bx * BOX), "r"(b) : "memory");
+                }
             }
         } else {
             // 16-byte chunks: chunk c -> row c / (ROWB/16), part c % (ROWB/16); 128 threads, consecutive threads take consecutive chunks
@@ -99,9 +106,14 @@ __global__ void __launch_bounds__(128, 3)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
             if (tid == 0) {
-                for (int bx = 0; bx < M / BOX; ++bx)
-                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                 ::"l"((uint64_t)&tout), "r"(s32(S + bx * BOX * ROWB)), "r"(dt * 8), "r"(r), "r"(bx * BOX), "r"(b) : "memory");
+                for (int bx = 0; bx < M / BOX; ++bx) {
+                    if (LD == 4)
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+                                     ::"l"((uint64_t)&tout), "r"(s32(S + bx * BOX * ROWB)), "r"(dt * 8), "r"(r), "r"(bx * BOX), "r"(b), "l"(pol) : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"((uint64_t)&tout), "r"(s32(S + bx * BOX * ROWB)), "r"(dt * 8), "r"(r), "r"(bx * BOX), "r"(b) : "memory");
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {
@@ -160,7 +172,7 @@ void run(EncFn enc, char* x, char* y, int B, int T, int D) {
     size_t bad = 0; for (size_t i = 0; i < n; ++i) bad += hx[i] != hy[i];
     free(hx); free(hy);
     double bytes = (double)n * 2;
-    printf("rowB=%2d load=%s store=%s : %.3f ms  %.0f GB/s (read+write)  mismatches=%zu  (%s)\n", ROWB, LD == 0 ? "TMA" : LD == 1 ? "LSU(cp.async16)" : LD == 2 ? "LSU(cp.async16.L2::128B)" : "LSU(cp.async16.L2::256B)", ST ? "LSU(st.global)" : "TMA",
+    printf("rowB=%2d load=%s store=%s : %.3f ms  %.0f GB/s (read+write)  mismatches=%zu  (%s)\n", ROWB, LD == 0 ? "TMA" : LD == 4 ? "TMA(evict_first ld+st)" : LD == 1 ? "LSU(cp.async16)" : LD == 2 ? "LSU(cp.async16.L2::128B)" : "LSU(cp.async16.L2::256B)", ST ? "LSU(st.global)" : "TMA",
            best, bytes / best / 1e6, bad, cudaGetErrorString(cudaGetLastError()));
 }
 
@@ -176,6 +188,7 @@ int main() {
     char *x, *y; cudaMalloc(&x, (size_t)B * T * D * 4); cudaMalloc(&y, (size_t)B * T * D * 4);
     fill<<<1024, 256>>>((uint32_t*)x, (size_t)B * T * D);
     run<32, 0, 0>(enc, x, y, B, T, D);
+    run<32, 4, 0>(enc, x, y, B, T, D);
     run<32, 1, 0>(enc, x, y, B, T, D);
     run<32, 0, 1>(enc, x, y, B, T, D);
     run<32, 1, 1>(enc, x, y, B, T, D);
@@ -183,7 +196,7 @@ int main() {
     run<32, 3, 0>(enc, x, y, B, T, D);
     run<32, 2, 1>(enc, x, y, B, T, D);
     run<16, 0, 0>(enc, x, y, B, T, D);
-    run<16, 1, 0>(enc, x, y, B, T, D);
+    run<16, 4, 0>(enc, x, y, B, T, D);
     run<16, 0, 1>(enc, x, y, B, T, D);
     run<16, 2, 0>(enc, x, y, B, T, D);
     return 0;
