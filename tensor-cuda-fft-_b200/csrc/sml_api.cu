@@ -64,6 +64,14 @@ std::map<int, DeviceState> g_dev;
 int device_state(DeviceState** out, int* dev_out) {
     int dev = 0;
     SML_CUDA(cudaGetDevice(&dev));
+    // Bind the device's primary context to THIS thread before any driver-API call (cuTensorMapEncodeTiled returns
+    // CUDA_ERROR_INVALID_CONTEXT otherwise): PyTorch's autograd worker threads reach sml_backward without ever
+    // having made a context-binding runtime call of their own.
+    static thread_local int bound_dev = -1;
+    if (bound_dev != dev) {
+        SML_CUDA(cudaFree(nullptr));
+        bound_dev = dev;
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     DeviceState& st = g_dev[dev];
     if (st.sm_count == 0) {

@@ -349,6 +349,18 @@ def test_full_size_properties(pkg, dev, B, T, D, dtype):
     assert hi <= (1e-9 if dtype == torch.float32 else 1e-3) * lo
 
 
+def test_fresh_process_smoke():
+    # a fresh interpreter: the FIRST library call of the autograd worker thread is sml_backward, which must bind the CUDA
+    # context itself before the driver-API tensor-map encode (regression: CUDA_ERROR_INVALID_CONTEXT)
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "smoke ok" in res.stdout
+
+
 def test_long_context_column(pkg, dev):
     # BASELINE config 5 top end: T = 128K, D = 1024 geometry on a narrow slice (R = 128 passes)
     B, T, D, Fn = 1, 131072, 32, 512
