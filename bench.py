@@ -32,6 +32,7 @@ if ROOT not in sys.path:
 
 import torch
 
+print_line = print       # replaced in main(): the JSON line is held back until fd 1 is restored
 METRIC = "spectral_mixing_fwd_bwd_tokens_per_sec"
 UNIT = "tokens/s"
 CFG = {"B": 16, "T": 8192, "D": 768}      # BASELINE.json configs[1]
@@ -99,7 +100,7 @@ def run_reference_arm(args):
                                    f"x=({B},{T},{D}) fwd+bwd, mean of {n} steps"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print_line(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -365,17 +366,32 @@ def run_ours(args):
             "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_step": roofline_step,
             "e2e": e2e, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        print_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: everything else a library prints there (e.g. NCCL's version banner) is sent
+    # to stderr by pointing fd 1 at fd 2 for the duration of the run.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    global print_line
+    print_line = lines.append
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        print(ln, flush=True)
 
 
 if __name__ == "__main__":

@@ -91,6 +91,39 @@ def run_wirtinger_cases(ref_w, seed):
     return out
 
 
+def run_lm_case(seed):
+    """SpectralLanguageModel (byte_spectral_model.py:105-161), the one reference LM that contains the layer: logits, next-byte
+    cross-entropy and a few parameter gradients for a small dropout-free configuration."""
+    import types
+    ref_sl = load_reference("spectral_layers")
+    pkg = types.ModuleType("fft_tensor")       # the model file does `from fft_tensor.spectral_layers import SpectralMLPBlock`
+    pkg.__path__ = []
+    sys.modules["fft_tensor"], sys.modules["fft_tensor.spectral_layers"] = pkg, ref_sl
+    ref_bm = load_reference("byte_spectral_model")
+    torch.manual_seed(seed)
+    E, L, T, B = 32, 2, 64, 2
+    model = ref_bm.SpectralLanguageModel(embed_dim=E, num_layers=L, max_seq_len=T, dropout=0.0)
+    with torch.no_grad():     # move the filters and the band weights off their trivial initial values
+        for blk in model.layers:
+            blk.spectral_mix.weight_real.normal_()
+            blk.spectral_mix.weight_imag.normal_()
+            blk.spectral_mix.bias.normal_()
+        model.byte_encoder.freq_bands.uniform_(0.5, 1.5)
+    ids = torch.randint(0, 256, (B, T))
+    emb = model.byte_encoder(ids)
+    logits = model(ids)
+    loss = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, 256), ids[:, 1:].reshape(-1))
+    loss.backward()
+    out = {"ids": ids.numpy(), "emb": emb.detach().numpy(), "logits": logits.detach().numpy(), "loss": np.float64(loss.item()),
+           "cfg": np.array([E, L, T, B], dtype=np.int64)}
+    for k, v in model.state_dict().items():
+        out["sd." + k] = v.numpy()
+    for name in ("layers.0.spectral_mix.weight_real", "layers.0.spectral_mix.weight_imag", "layers.0.spectral_mix.bias",
+                 "layers.1.spectral_mix.weight_real", "byte_encoder.freq_bands", "output.weight", "layers.0.norm1.weight"):
+        out["grad." + name] = dict(model.named_parameters())[name].grad.numpy()
+    return out
+
+
 def main():
     if not os.path.isdir(REF_ROOT):
         sys.exit(f"{REF_ROOT} not found: golden vectors can only be regenerated where the reference is mounted")
@@ -109,6 +142,7 @@ def main():
     np.savez_compressed(os.path.join(OUT_DIR, "layer_nonlearnable.npz"), x=x.numpy(), y=lay(x).numpy(),
                         n_params=np.int64(sum(p.numel() for p in lay.parameters())))
     np.savez_compressed(os.path.join(OUT_DIR, "wirtinger.npz"), **run_wirtinger_cases(ref_w, seed=4242))
+    np.savez_compressed(os.path.join(OUT_DIR, "lm_small.npz"), **run_lm_case(seed=31337))
     # parameter-count known answer, BENCHMARKS.md:86
     n = sum(p.numel() for p in ref_sl.SpectralMixingLayer(256).parameters())
     assert n == 65792, n

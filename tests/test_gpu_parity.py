@@ -349,6 +349,30 @@ def test_full_size_properties(pkg, dev, B, T, D, dtype):
     assert hi <= (1e-9 if dtype == torch.float32 else 1e-3) * lo
 
 
+def test_language_model_golden(pkg, dev, golden_dir):
+    # SpectralLanguageModel (reference byte_spectral_model.py:105-161) with the fused layer inside: logits, loss and gradients
+    # against the unmodified reference run on the CPU (tests/golden/lm_small.npz)
+    z = np.load(os.path.join(golden_dir, "lm_small.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    E, L, T, _ = (int(v) for v in z["cfg"])
+    model = pkg.SpectralLanguageModel(embed_dim=E, num_layers=L, max_seq_len=T, dropout=0.0)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev)
+    ids = torch.from_numpy(z["ids"]).to(dev)
+    logits = model(ids)
+    loss = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, 256), ids[:, 1:].reshape(-1))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert orc.rel_l2(logits.detach().cpu().numpy(), z["logits"]) <= 1e-4
+    assert abs(loss.item() - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
+    params = dict(model.named_parameters())
+    for k in z.files:
+        if k.startswith("grad."):
+            assert orc.rel_l2(params[k[5:]].grad.cpu().numpy(), z[k]) <= 1e-3, k
+    text = model.generate("ab", max_new_bytes=3)
+    assert text.startswith("ab") and len(text) >= 3
+
+
 def test_fresh_process_smoke():
     # a fresh interpreter: the FIRST library call of the autograd worker thread is sml_backward, which must bind the CUDA
     # context itself before the driver-API tensor-map encode (regression: CUDA_ERROR_INVALID_CONTEXT)
