@@ -152,6 +152,11 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def _collective_path():
+    from tensor_cuda_fft_b200 import distributed as d
+    return d.LAST_ALLREDUCE_PATH
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -360,7 +365,7 @@ def run_ours(args):
                                    f"k={k} live bins, randn x/g/filter, dropout 0 (BASELINE.json configs[1])",
                        "global_batch": world * B, "seq_len": T, "embed_dim": D, "parallelism": f"batch-sharded x{world}",
                        "plan": plan, "l2": f"inputs larger than L2 ({2 * B * T * D * esz / 1e6:.0f} MB read per step vs 126 MB), no flush",
-                       "collective": "none" if world == 1 else "1 NCCL all-reduce(sum) of [gw_re|gw_im|gb] per step"},
+                       "collective": "none" if world == 1 else f"1 all-reduce(sum) of [gw_re|gw_im|gb] per step ({_collective_path()})"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_step": roofline_step,
