@@ -149,6 +149,11 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
             }
             // (P = 6, i.e. 48-byte rows and 2 CTAs of 6 warps per SM, was measured at 0.320 ms per forward launch against
             //  0.197 ms for P = 4: rows that are not a multiple of the 32-byte sector straddle sectors on loads and stores.)
+            // TMA landing tiles: two (loads run two passes ahead) pay off for the small sub-transforms (measured at
+            // (32, 8192, 256) fp32: 0.152 vs 0.167 ms per forward launch); at M = 1024 one tile is faster (bf16 cfg-2: 0.203 vs
+            // 0.208 ms, cfg-3 fp32: 0.592 vs 0.597 ms) and for fp32 two do not fit next to three CTAs per SM anyway.
+            p.xb = p.NR <= 16 ? 2 : 1;
+            if (const char* e = getenv("SML_FAST_XB")) p.xb = atoi(e) == 2 ? 2 : 1;   // tuning knob
             if (p.NR == 32) {   // M = 1024: warp-specialised kernel, 8 pairs (64-byte TMA rows) per CTA, one CTA per SM
                 p.ws = false;   // experimental (opt-in) until it is parity-green on the GPU
                 if (const char* e = getenv("SML_FAST_WS")) p.ws = atoi(e) != 0;   // tuning knob: 1 = warp-specialised kernel

@@ -158,7 +158,7 @@ struct PairIO<__nv_bfloat16> {
     }
 };
 
-template <int NR, int P, typename IO>
+template <int NR, int P, typename IO, int XB = 1>
 struct FastCfg {
     static constexpr int NT = NR * P;
     static constexpr int M = NR * NR;
@@ -168,7 +168,7 @@ struct FastCfg {
     static constexpr uint32_t LOAD_BYTES = (uint32_t)M * 2u * P * sizeof(IO);            // X: one TMA stage, dense [M][2P]
     static constexpr uint32_t XBUF_BYTES = (LOAD_BYTES + 127u) & ~127u;
     static constexpr uint32_t YBUF_BYTES = ((uint32_t)NT * XS * sizeof(cf) + 127u) & ~127u;   // Y: exchange [NT][XS]
-    static constexpr size_t SMEM_BYTES = (size_t)XBUF_BYTES + YBUF_BYTES + 2u * NR * sizeof(cf) + 2 * sizeof(uint64_t);   // mbarrier + arrive counter
+    static constexpr size_t SMEM_BYTES = (size_t)XB * XBUF_BYTES + YBUF_BYTES + 2u * NR * sizeof(cf) + 4 * sizeof(uint64_t);   // 2 mbarriers + 2 drain counters
 };
 
 // v[i] *= (or *= conj of) base0 * step^i for i in [0, NR): twiddle powers generated in registers, 8 at a time.
@@ -319,25 +319,34 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-// CPA selects the load path: false = TMA tile loads issued by one thread; true = per-thread 16-byte cp.async.cg
-// (measured on B200, tools/microbench/ldst_stream.cu: with 32-byte rows a TMA-load + TMA-store stream of the cfg-2 tensor
-// takes 0.183 ms, cp.async loads + TMA stores 0.157 ms; with 16-byte rows (bf16, P = 4) TMA loads win, 0.115 vs 0.18 ms).
-template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, bool CPA>
+// XB = number of TMA landing tiles.  XB = 1: the load of pass r+1 is issued when pass r has been drained and has one pass
+// of compute to land.  XB = 2 (where shared memory allows three CTAs per SM with it, i.e. bf16 I/O at M = 1024 and the
+// small sub-transforms): loads run two passes ahead; during synthesis one tile is the store staging buffer while the other
+// already receives pass 0 of the next work item.
+// (A per-thread cp.async.cg load path was measured too: 0.157 vs 0.183 ms in a copy-only stream of 32-byte rows,
+//  tools/microbench/ldst_stream.cu, but 0.227 vs 0.198 ms inside this kernel, where the copies compete with the exchange
+//  traffic for the LSU / shared-memory pipe -- TMA stays the load path.)
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, int XB>
 __global__ void __launch_bounds__(NR* P, MINB)
     sml_fast_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                     const FastParams prm) {
-    using C = FastCfg<NR, P, IO>;
-    constexpr int NT = C::NT, M = C::M, XS = C::XS;
+    using C = FastCfg<NR, P, IO, XB>;
+    static_assert(XB == 1 || XB == 2, "one or two landing tiles");
+    constexpr int NT = C::NT, XS = C::XS;
     constexpr int NJ = 2 * KJ;   // live f2 columns held per thread: [0,KJ) and [NR-KJ, NR)
     static_assert(NJ <= NR, "band wider than the sub-transform");
     static_assert(NT % 32 == 0 && 32 % NR == 0, "freq-side partner bin must live in the same warp");
 
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* const xbuf = smem;                                                    // landing / staging
-    cf* const ybuf = reinterpret_cast<cf*>(smem + C::XBUF_BYTES);                        // exchange [NT][XS]
-    cf* const cj = reinterpret_cast<cf*>(smem + C::XBUF_BYTES + C::YBUF_BYTES);          // [2][NR]  W_T^{NR r f2s}
-    uint64_t* const mbar = reinterpret_cast<uint64_t*>(cj + 2 * NR);                     // [1]
-    unsigned int* const xdone = reinterpret_cast<unsigned int*>(mbar + 1);               // warps that have drained X
+    unsigned char* const xbuf0 = smem;                                                   // XB landing / staging tiles
+    cf* const ybuf = reinterpret_cast<cf*>(smem + XB * C::XBUF_BYTES);                   // exchange [NT][XS]
+    cf* const cj = reinterpret_cast<cf*>(smem + XB * C::XBUF_BYTES + C::YBUF_BYTES);     // [2][NR]  W_T^{NR r f2s}
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(cj + 2 * NR);                     // [2] one per landing tile
+    unsigned int* const xdone = reinterpret_cast<unsigned int*>(mbar + 2);               // [2] warps that have drained X[slot]
+    // load n lands in tile n % XB and completes phase n / XB of that tile's mbarrier
+    auto xslot = [&](int n) -> int { return XB == 2 ? (n & 1) : 0; };
+    auto xbuf = [&](int n) -> unsigned char* { return xbuf0 + (size_t)xslot(n) * C::XBUF_BYTES; };
+    auto xparity = [&](int n) -> uint32_t { return XB == 2 ? (((uint32_t)n >> 1) & 1u) : ((uint32_t)n & 1u); };
 
     const int tid = threadIdx.x;
     const int tp = tid % P, tm2 = tid / P;      // time-side mapping
@@ -348,49 +357,21 @@ __global__ void __launch_bounds__(NR* P, MINB)
     const int my_ntiles = (prm.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_loads = my_ntiles * R;
 
-    // cp.async path: a warp's threads (p = tid % P, m2 = tid / P) read exactly the rows m with m % NR in
-    // [wm2, wm2 + 32 / P), all 2P channels -- so each warp owns its rows of X and refills them by itself, right after its
-    // own drain, with no CTA-wide synchronisation.  Every thread arrives on the mbarrier when its copies have landed.
-    auto issue_load_cpa = [&](int L) {   // all threads (warp-collective)
-        if (L >= total_loads) return;
-        constexpr int CPR = 2 * P * (int)sizeof(IO) / 16;        // 16-byte chunks per row
-        constexpr int RPW = 32 / P;                              // row residues owned by one warp
-        constexpr int NCH = NR * RPW * CPR;                      // chunks per warp and pass
-        static_assert(CPR >= 1 && NCH % 32 == 0, "cp.async load path needs rows of at least 16 bytes");
-        const int it = L / R, r = L - it * R;
-        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-        const int b = tile / prm.ntd, dt = tile - b * prm.ntd;
-        const int lane = tid & 31, wm2 = (tid >> 5) * RPW;
-        const size_t row_bytes = (size_t)D * sizeof(IO);
-        const char* src0 = reinterpret_cast<const char*>(prm.in) + ((size_t)b * T + r) * row_bytes + (size_t)dt * 2 * P * sizeof(IO);
-        const int valid_bytes = (D - dt * 2 * P) * (int)sizeof(IO);   // channel-tile tail: chunks past D are zero-filled
-#pragma unroll
-        for (int i = 0; i < NCH / 32; ++i) {
-            const int q = lane + 32 * i;
-            const int part = q % CPR, j = (q / CPR) % RPW, m1 = q / (CPR * RPW);
-            const int row = NR * m1 + wm2 + j;
-            const bool ok = part * 16 < valid_bytes;
-            const char* src = src0 + (size_t)row * R * row_bytes + (ok ? part * 16 : 0);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
-                         ::"r"(smem_u32(xbuf + (size_t)row * 2 * P * sizeof(IO) + part * 16)), "l"(src), "r"(ok ? 16 : 0) : "memory");
-        }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
-    };
     auto issue_load = [&](int L) {   // thread 0 only.  load L = (tile L / R, pass L % R) -> X
         if (L >= total_loads) return;
         const int it = L / R, r = L - it * R;
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         const int b = tile / prm.ntd, dt = tile - b * prm.ntd;
         fence_proxy_async();
-        mbar_expect_tx(mbar, C::LOAD_BYTES);
+        mbar_expect_tx(mbar + xslot(L), C::LOAD_BYTES);
 #pragma unroll
         for (int bx = 0; bx < C::NBOX; ++bx)
-            tma_load_4d(xbuf + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), &tmap_in, mbar, dt * 2 * P, r, bx * C::BOXROWS, b);
+            tma_load_4d(xbuf(L) + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), &tmap_in, mbar + xslot(L), dt * 2 * P, r, bx * C::BOXROWS, b);
     };
-    auto issue_store = [&](int b, int dt, int r) {   // thread 0 only: X -> rows r + R*m of the output
+    auto issue_store = [&](const unsigned char* stage, int b, int dt, int r) {   // thread 0 only: staging tile -> rows r + R*m
 #pragma unroll
         for (int bx = 0; bx < C::NBOX; ++bx)
-            tma_store_4d(&tmap_out, xbuf + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), dt * 2 * P, r, bx * C::BOXROWS, b);
+            tma_store_4d(&tmap_out, stage + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), dt * 2 * P, r, bx * C::BOXROWS, b);
         tma_store_commit();
     };
     // uniform twiddle of pass r for column f2 = tid (threads < NR): W_T^{NR r f2s}
@@ -400,13 +381,17 @@ __global__ void __launch_bounds__(NR* P, MINB)
     };
 
     if (tid == 0) {
-        mbar_init(mbar, CPA ? NT : 1);
+        mbar_init(mbar, 1);
+        mbar_init(mbar + 1, 1);
         fence_mbar_init();
-        *xdone = 0u;
+        xdone[0] = 0u;
+        xdone[1] = 0u;
     }
     __syncthreads();
-    if constexpr (CPA) issue_load_cpa(0);
-    else if (tid == 0) issue_load(0);
+    if (tid == 0) {
+        issue_load(0);
+        if constexpr (XB == 2) issue_load(1);
+    }
 
     int L = 0;      // loads consumed so far
     int slot = 0;   // cj slot of the current pass
@@ -429,22 +414,20 @@ __global__ void __launch_bounds__(NR* P, MINB)
                 cjv = cj_load(r);
                 if (r + 1 == R) cjn = cj_load(0);   // first synthesis pass
             }
-            mbar_wait(mbar, (uint32_t)L & 1u, prm.dbg, 1u, (uint32_t)L);
+            mbar_wait(mbar + xslot(L), xparity(L), prm.dbg, 1u, (uint32_t)L);
             cf v[NR];
             {
-                const IO* src = reinterpret_cast<const IO*>(xbuf) + tm2 * 2 * P + 2 * tp;
+                const IO* src = reinterpret_cast<const IO*>(xbuf(L)) + tm2 * 2 * P + 2 * tp;
 #pragma unroll
                 for (int m1 = 0; m1 < NR; ++m1) v[m1] = PairIO<IO>::load_s(src + m1 * NR * 2 * P);
             }
-            // the last warp to drain X re-arms it with the next pass right away (X is the staging buffer after the
-            // last pass, so nothing is prefetched across the analysis/synthesis boundary)
+            // the last warp to drain the tile re-arms it right away with the next load that lands there (XB ahead).  The tile
+            // of a work item's last pass becomes the store staging buffer instead and is re-armed after the last store.
             if (r + 1 < R) {
                 __syncwarp();
-                if constexpr (CPA) {
-                    issue_load_cpa(L + 1);   // this warp's own rows: no other warp reads them
-                } else if ((tid & 31) == 0) {
+                if ((tid & 31) == 0) {
                     __threadfence_block();
-                    if ((atomicAdd(xdone, 1u) % (NT / 32)) == NT / 32 - 1) issue_load(L + 1);
+                    if ((atomicAdd(xdone + xslot(L), 1u) % (NT / 32)) == NT / 32 - 1) issue_load(L + XB);
                 }
             }
             Dft<NR, -1>::run(v);   // over m1 -> f1
@@ -482,6 +465,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
         spectral_mid_phase<NR, KJ, BWD>(acc, prm, b, dt * 2 * P + 2 * fp2, ff1, tid & 31);
 
         // ===================== synthesis: transpose of analysis; rows leave through a TMA store from X =====================
+        unsigned char* const stage = xbuf(L - 1);   // tile of this work item's last load, drained by every warp (barrier (A'))
         const int td0 = dt * 2 * P + 2 * tp;   // time-side channel pair
         cf bias2 = cf{0.f, 0.f};
         if constexpr (!BWD) {
@@ -526,22 +510,18 @@ __global__ void __launch_bounds__(NR* P, MINB)
             }
             Dft<NR, +1>::run(v);   // over f1 -> m1
             {
-                IO* dst = reinterpret_cast<IO*>(xbuf) + tm2 * 2 * P + 2 * tp;
+                IO* dst = reinterpret_cast<IO*>(stage) + tm2 * 2 * P + 2 * tp;
 #pragma unroll
                 for (int m1 = 0; m1 < NR; ++m1) PairIO<IO>::store_s(dst + m1 * NR * 2 * P, cadd(v[m1], bias2));
             }
             fence_proxy_async();
             __syncthreads();   // (C') staging tile complete: the store drains while the next pass computes
-            if (tid == 0) issue_store(b, dt, r);
+            if (tid == 0) issue_store(stage, b, dt, r);
             slot ^= 1;
         }
-        if constexpr (CPA) {
-            if (tid == 0) tma_store_wait_read();
-            __syncthreads();         // the last staging tile has left X
-            issue_load_cpa(L);       // pass 0 of the next tile
-        } else if (tid == 0) {
+        if (tid == 0) {
             tma_store_wait_read();
-            issue_load(L);   // pass 0 of the next tile
+            issue_load(L + XB - 1);   // the staging tile's next load: pass XB - 1 of the next work item
         }
     }
     if (tid == 0) tma_store_wait_all();

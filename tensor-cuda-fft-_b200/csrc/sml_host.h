@@ -15,6 +15,7 @@ struct Plan {
     int k = 0;
     int NR = 0, KJ = 0, P = 0, M = 0, R = 0;
     int ctas_per_sm = 1;
+    int xb = 1;        // TMA landing tiles (2 only where the kernel variant was built with them)
     bool ws = false;   // warp-specialised 512-thread kernel (NR = 32 only)
 };
 

@@ -14,15 +14,15 @@ namespace sml_host {
         if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e));    \
     } while (0)
 
-template <int NR, int KJ, int P, int MINB, typename IO, bool BWD>
-int launch_fast_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
-                     cudaStream_t stream) {
-    using C = sml::FastCfg<NR, P, IO>;
-    // In a copy-only stream cp.async loads beat TMA loads for rows of >= 32 bytes (tools/microbench/ldst_stream.cu), but
-    // measured in the real kernel (cfg-2 fp32): cp.async loads 0.227 ms vs TMA loads 0.198 ms per forward launch -- the
-    // per-thread copies compete with the exchange traffic for the LSU/shared-memory pipe, so TMA stays the load path.
-    constexpr bool CPA = false;
-    auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD, CPA>;
+// two landing tiles fit wherever MINB CTAs per SM still fit into 227 KB of shared memory with them
+template <int NR, int P, int MINB, typename IO>
+constexpr bool xb2_fits() { return (sml::FastCfg<NR, P, IO, 2>::SMEM_BYTES + 1024) * MINB <= 227u * 1024u; }
+
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, int XB>
+int launch_fast_xb(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
+                   cudaStream_t stream) {
+    using C = sml::FastCfg<NR, P, IO, XB>;
+    auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD, XB>;
     static std::once_flag once;   // one per instantiation
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] {
@@ -33,6 +33,15 @@ int launch_fast_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, cons
     count_launch();
     SML_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD>
+int launch_fast_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
+                     cudaStream_t stream, int xb) {
+    if constexpr (xb2_fits<NR, P, MINB, IO>()) {
+        if (xb == 2) return launch_fast_xb<NR, KJ, P, MINB, IO, BWD, 2>(map_in, map_out, prm, grid, stream);
+    }
+    return launch_fast_xb<NR, KJ, P, MINB, IO, BWD, 1>(map_in, map_out, prm, grid, stream);
 }
 
 template <int KJ, typename IO, bool BWD>
@@ -61,7 +70,7 @@ int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map
         return launch_ws_inst<16, IO, BWD>(map_in, map_out, prm, grid, stream);
     }
 #define SML_CASE(NR_, KJ_, P_, MINB_) \
-    if (p.NR == NR_ && p.KJ == KJ_ && p.P == P_ && p.ctas_per_sm == MINB_) return launch_fast_inst<NR_, KJ_, P_, MINB_, IO, BWD>(map_in, map_out, prm, grid, stream);
+    if (p.NR == NR_ && p.KJ == KJ_ && p.P == P_ && p.ctas_per_sm == MINB_) return launch_fast_inst<NR_, KJ_, P_, MINB_, IO, BWD>(map_in, map_out, prm, grid, stream, p.xb);
     SML_CASE(32, 8, 4, 3)
     SML_CASE(32, 12, 4, 3)
     SML_CASE(32, 16, 4, 2)

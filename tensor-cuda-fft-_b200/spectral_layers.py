@@ -18,6 +18,22 @@ from . import _native
 _IO_DTYPES = {torch.float32: _native.DTYPE_F32, torch.bfloat16: _native.DTYPE_BF16}
 
 
+_SHAPE_CACHE = {}
+
+
+def _shape_info(B: int, T: int, D: int, Fn: int, io: int):
+    """(fast_path, xlow_bytes, workspace_bytes) of a problem, cached: three ctypes round trips per call otherwise."""
+    key = (B, T, D, Fn, io)
+    info = _SHAPE_CACHE.get(key)
+    if info is None:
+        lib = _native.lib()
+        info = (_native.plan(B, T, D, Fn, io)["path"] == "fast", int(lib.sml_xlow_bytes(B, T, D, Fn)),
+                int(lib.sml_workspace_bytes(B, T, D, Fn, io)))
+        if len(_SHAPE_CACHE) < 4096:
+            _SHAPE_CACHE[key] = info
+    return info
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -48,10 +64,9 @@ class _SpectralMixFn(torch.autograd.Function):
         bs = None if bias is None else bias.detach().contiguous().float()
         y = torch.empty_like(xc)
         need_filter_grad = any(ctx.needs_input_grad[1:])
-        plan = _native.plan(B, T, D, Fn, io)
+        fast_path, nbytes, _ = _shape_info(B, T, D, Fn, io)
         xlow = None
-        if need_filter_grad or plan["path"] == "generic":
-            nbytes = lib.sml_xlow_bytes(B, T, D, Fn)
+        if need_filter_grad or not fast_path:
             xlow = torch.empty(max(nbytes // 8, 1), dtype=torch.complex64, device=x.device)
         with torch.cuda.device(x.device):
             _native.check(lib.sml_forward(_ptr(xc), _ptr(wr), _ptr(wi), _ptr(bs), _ptr(y), _ptr(xlow),
@@ -59,7 +74,7 @@ class _SpectralMixFn(torch.autograd.Function):
         ctx.save_for_backward(wr, wi, xlow if need_filter_grad else None)
         ctx.shape = (B, T, D, Fn, io)
         ctx.has_bias = bias is not None
-        ctx.fast_path = plan["path"] == "fast"
+        ctx.fast_path = fast_path
         ctx.param_dtypes = (w_re.dtype, w_im.dtype, None if bias is None else bias.dtype)
         return y
 
@@ -82,7 +97,7 @@ class _SpectralMixFn(torch.autograd.Function):
             gwi = flat[D * Fn: 2 * D * Fn].view(D, Fn)
             gb = flat[2 * D * Fn:]
         # fast path: scratch only for the filter-gradient terms; generic path: always (low-band spectrum of g)
-        ws_bytes = lib.sml_workspace_bytes(B, T, D, Fn, io) if (want or not ctx.fast_path) else 0
+        ws_bytes = _shape_info(B, T, D, Fn, io)[2] if (want or not ctx.fast_path) else 0
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gc.device) if ws_bytes else None
         with torch.cuda.device(gc.device):
             _native.check(lib.sml_backward(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gx), _ptr(gwr), _ptr(gwi),
