@@ -163,12 +163,13 @@ struct FastCfg {
     static constexpr int NT = NR * P;
     static constexpr int M = NR * NR;
     static constexpr int XS = NR + 2;    // exchange row stride (complex): rows stay 16-byte aligned (128-bit row access)
+    static constexpr int CJN = 2 * NR;   // pass twiddles per slot: one per band column (up to 2 NR columns, see KJ)
     static constexpr int BOXROWS = M < 256 ? M : 256;
     static constexpr int NBOX = M / BOXROWS;
     static constexpr uint32_t LOAD_BYTES = (uint32_t)M * 2u * P * sizeof(IO);            // X: one TMA stage, dense [M][2P]
     static constexpr uint32_t XBUF_BYTES = (LOAD_BYTES + 127u) & ~127u;
     static constexpr uint32_t YBUF_BYTES = ((uint32_t)NT * XS * sizeof(cf) + 127u) & ~127u;   // Y: exchange [NT][XS]
-    static constexpr size_t SMEM_BYTES = (size_t)XB * XBUF_BYTES + YBUF_BYTES + 2u * NR * sizeof(cf) + 4 * sizeof(uint64_t);   // 2 mbarriers + 2 drain counters
+    static constexpr size_t SMEM_BYTES = (size_t)XB * XBUF_BYTES + YBUF_BYTES + 2u * CJN * sizeof(cf) + 4 * sizeof(uint64_t);   // 2 mbarriers + 2 drain counters
 };
 
 // v[i] *= (or *= conj of) base0 * step^i for i in [0, NR): twiddle powers generated in registers, 8 at a time.
@@ -300,7 +301,12 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
         }
         const float h = 0.5f * prm.invT;
         cf c = cf{h * (a0.re - a1.im), h * (a0.im + a1.re)};
-        if (af == 0) c = cf{a0.re * prm.invT, a1.re * prm.invT};   // DC bin
+        if (af == 0) {   // DC bin; the bias (reference :116) rides on it: a constant in time is a DC term of y_d + i y_{d+1}
+            c = cf{a0.re * prm.invT, a1.re * prm.invT};
+            if constexpr (!BWD) {
+                if (prm.bias != nullptr && pvalid) c = cf{c.re + __ldg(prm.bias + d0), c.im + __ldg(prm.bias + d0 + 1)};
+            }
+        }
         acc[j] = c;
         // hand the value for the mirror bin -fs to its owner (the partner does the same for this thread)
         const cf cn = cf{h * (a0.re + a1.im), h * (a1.re - a0.im)};
@@ -334,14 +340,19 @@ __global__ void __launch_bounds__(NR* P, MINB)
     static_assert(XB == 1 || XB == 2, "one or two landing tiles");
     constexpr int NT = C::NT, XS = C::XS;
     constexpr int NJ = 2 * KJ;   // live f2 columns held per thread: [0,KJ) and [NR-KJ, NR)
-    static_assert(NJ <= NR, "band wider than the sub-transform");
+    // KJ <= NR/2: the band (2k-1 bins) fits into one period of the sub-transform, every sub-bin f2 carries at most one band
+    // column.  NR/2 < KJ <= NR ("wide band", k <= M): a sub-bin f1 + NR f2 carries two band bins, fs = f1 + NR f2 >= 0 and
+    // fs - M < 0, i.e. columns j = f2 and j = f2 + NJ - NR accumulate the same DFT output with different pass twiddles --
+    // this is what lets T = 2k (full half-spectrum, e.g. T = 512 with embed >= 512) run with M = T/2, R = 2.
+    static_assert(NJ <= 2 * NR, "band wider than two periods of the sub-transform");
     static_assert(NT % 32 == 0 && 32 % NR == 0, "freq-side partner bin must live in the same warp");
+    constexpr int CJN = C::CJN;
 
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* const xbuf0 = smem;                                                   // XB landing / staging tiles
     cf* const ybuf = reinterpret_cast<cf*>(smem + XB * C::XBUF_BYTES);                   // exchange [NT][XS]
-    cf* const cj = reinterpret_cast<cf*>(smem + XB * C::XBUF_BYTES + C::YBUF_BYTES);     // [2][NR]  W_T^{NR r f2s}
-    uint64_t* const mbar = reinterpret_cast<uint64_t*>(cj + 2 * NR);                     // [2] one per landing tile
+    cf* const cj = reinterpret_cast<cf*>(smem + XB * C::XBUF_BYTES + C::YBUF_BYTES);     // [2][CJN]  W_T^{NR r f2s(j)}
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(cj + 2 * CJN);                    // [2] one per landing tile
     unsigned int* const xdone = reinterpret_cast<unsigned int*>(mbar + 2);               // [2] warps that have drained X[slot]
     // load n lands in tile n % XB and completes phase n / XB of that tile's mbarrier
     auto xslot = [&](int n) -> int { return XB == 2 ? (n & 1) : 0; };
@@ -374,9 +385,9 @@ __global__ void __launch_bounds__(NR* P, MINB)
             tma_store_4d(&tmap_out, stage + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), dt * 2 * P, r, bx * C::BOXROWS, b);
         tma_store_commit();
     };
-    // uniform twiddle of pass r for column f2 = tid (threads < NR): W_T^{NR r f2s}
+    // uniform twiddle of pass r for band column j = tid (threads < NJ): W_T^{NR r f2s}, f2s = j (j < KJ) or j - NJ
     auto cj_load = [&](int r) -> float2 {
-        const int f2s = tid < NR / 2 ? tid : tid - NR;
+        const int f2s = tid < KJ ? tid : tid - NJ;
         return __ldg(gtab + ((NR * r * f2s) & (T - 1)));
     };
 
@@ -410,7 +421,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
             // twiddle seeds for this pass (consumed after the first DFT / after barrier (A))
             const float2 wb = __ldg(gtab + (R * tm2 + r));   // W_T^{R m2 + r}
             float2 cjv = make_float2(1.f, 0.f), cjn = make_float2(1.f, 0.f);
-            if (tid < NR) {
+            if (tid < NJ) {
                 cjv = cj_load(r);
                 if (r + 1 == R) cjn = cj_load(0);   // first synthesis pass
             }
@@ -438,9 +449,9 @@ __global__ void __launch_bounds__(NR* P, MINB)
 #pragma unroll
                 for (int h = 0; h < NR / 2; ++h) xrow[h] = make_float4(v[2 * h].re, v[2 * h].im, v[2 * h + 1].re, v[2 * h + 1].im);
             }
-            if (tid < NR) {
-                cj[slot * NR + tid] = cf{cjv.x, cjv.y};
-                if (r + 1 == R) cj[(slot ^ 1) * NR + tid] = cf{cjn.x, cjn.y};
+            if (tid < NJ) {
+                cj[slot * CJN + tid] = cf{cjv.x, cjv.y};
+                if (r + 1 == R) cj[(slot ^ 1) * CJN + tid] = cf{cjn.x, cjn.y};
             }
             __syncthreads();   // (B)
             {
@@ -450,11 +461,11 @@ __global__ void __launch_bounds__(NR* P, MINB)
             }
             Dft<NR, -1>::run(v);   // over m2 -> f2   (outputs outside the band are dead code)
             {
-                const cf* cjs = cj + slot * NR;
+                const cf* cjs = cj + slot * CJN;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     const int f2 = j < KJ ? j : NR - NJ + j;
-                    acc[j] = cmac(acc[j], v[f2], cjs[f2]);
+                    acc[j] = cmac(acc[j], v[f2], cjs[j]);
                 }
             }
             slot ^= 1;
@@ -466,26 +477,23 @@ __global__ void __launch_bounds__(NR* P, MINB)
 
         // ===================== synthesis: transpose of analysis; rows leave through a TMA store from X =====================
         unsigned char* const stage = xbuf(L - 1);   // tile of this work item's last load, drained by every warp (barrier (A'))
-        const int td0 = dt * 2 * P + 2 * tp;   // time-side channel pair
-        cf bias2 = cf{0.f, 0.f};
-        if constexpr (!BWD) {
-            if (prm.bias != nullptr && td0 < D) bias2 = cf{__ldg(prm.bias + td0), __ldg(prm.bias + td0 + 1)};
-        }
         for (int r = 0; r < R; ++r) {
             // twiddle seeds: v[m2] *= conj(W_T^{r f1} * (W_T^{R f1})^{m2})
             const float2 sr = __ldg(gtab + r * ff1);
             const float2 beta = __ldg(gtab + R * ff1);
             float2 cjn = make_float2(1.f, 0.f);
-            if (tid < NR && r + 1 < R) cjn = cj_load(r + 1);
+            if (tid < NJ && r + 1 < R) cjn = cj_load(r + 1);
             cf v[NR];
             {
-                const cf* cjs = cj + slot * NR;
+                const cf* cjs = cj + slot * CJN;
 #pragma unroll
                 for (int f2 = 0; f2 < NR; ++f2) v[f2] = cf{0.f, 0.f};
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     const int f2 = j < KJ ? j : NR - NJ + j;
-                    v[f2] = cmulc(acc[j], cjs[f2]);
+                    const cf term = cmulc(acc[j], cjs[j]);
+                    // wide band: the negative column j lands on a sub-bin that already holds its non-negative alias
+                    v[f2] = (j >= KJ && f2 < KJ) ? cadd(v[f2], term) : term;
                 }
             }
             Dft<NR, +1>::run(v);   // over f2 -> m2
@@ -496,7 +504,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
 #pragma unroll
                 for (int m2 = 0; m2 < NR; ++m2) xb[m2 * P * XS] = v[m2];
             }
-            if (tid < NR && r + 1 < R) cj[(slot ^ 1) * NR + tid] = cf{cjn.x, cjn.y};
+            if (tid < NJ && r + 1 < R) cj[(slot ^ 1) * CJN + tid] = cf{cjn.x, cjn.y};
             if (tid == 0 && r > 0) tma_store_wait_read();   // X may be overwritten after (B')
             __syncthreads();   // (B')
             {
@@ -512,7 +520,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
             {
                 IO* dst = reinterpret_cast<IO*>(stage) + tm2 * 2 * P + 2 * tp;
 #pragma unroll
-                for (int m1 = 0; m1 < NR; ++m1) PairIO<IO>::store_s(dst + m1 * NR * 2 * P, cadd(v[m1], bias2));
+                for (int m1 = 0; m1 < NR; ++m1) PairIO<IO>::store_s(dst + m1 * NR * 2 * P, v[m1]);
             }
             fence_proxy_async();
             __syncthreads();   // (C') staging tile complete: the store drains while the next pass computes

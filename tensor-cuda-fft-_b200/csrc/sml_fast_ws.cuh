@@ -156,11 +156,6 @@ __global__ void __launch_bounds__(512, 1)
             role_barrier(1, NTR);
             // ---------------- synthesis: Y -> iDFT over f1 -> +bias -> staging tile -> TMA store ----------------
             unsigned char* const stage = xbuf((L - 1) & 1);   // slot of the tile's last load (drained by every T warp)
-            const int td0 = dt * 2 * P + 2 * tp;
-            cf bias2 = cf{0.f, 0.f};
-            if constexpr (!BWD) {
-                if (prm.bias != nullptr && td0 < D) bias2 = cf{__ldg(prm.bias + td0), __ldg(prm.bias + td0 + 1)};
-            }
             for (int r = 0; r < R; ++r) {
                 cf v[NR];
                 mbar_wait(yfull, c & 1u, prm.dbg, 12u, c);
@@ -180,7 +175,7 @@ __global__ void __launch_bounds__(512, 1)
                 {
                     IO* dst = reinterpret_cast<IO*>(stage) + tm2 * 2 * P + 2 * tp;
 #pragma unroll
-                    for (int m1 = 0; m1 < NR; ++m1) PairIO<IO>::store_s(dst + m1 * NR * 2 * P, cadd(v[m1], bias2));
+                    for (int m1 = 0; m1 < NR; ++m1) PairIO<IO>::store_s(dst + m1 * NR * 2 * P, v[m1]);
                 }
                 fence_proxy_async();
                 role_barrier(1, NTR);                           // staging tile complete

@@ -42,6 +42,11 @@ def test_plan_selection(native):
     assert native.plan(2, 16, 64, 32)["k"] == 8                  # k = min(F, T//2)
     assert native.plan(2, 16, 64, 32)["path"] == "generic"       # sub-transform would not fit in T
     assert native.plan(2, 64, 32, 16) == {"path": "fast", "M": 64, "R": 1, "k": 16}
+    # wide band (k <= M < 2k): full half-spectrum shapes run with M = T/2, R = 2
+    assert native.plan(4, 512, 768, 384) == {"path": "fast", "M": 256, "R": 2, "k": 256}
+    assert native.plan(2, 128, 256, 128) == {"path": "fast", "M": 64, "R": 2, "k": 64}
+    assert native.plan(2, 512, 384, 192) == {"path": "fast", "M": 256, "R": 2, "k": 192}
+    assert native.plan(2, 2048, 2048, 1024)["path"] == "generic"   # k = 1024 > 512: no kernel variant
     assert native.plan(16, 8192, 768, 384, native.DTYPE_BF16)["path"] == "fast"
 
 

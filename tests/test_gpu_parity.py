@@ -95,7 +95,11 @@ SHAPES = [
     (2, 384, 48, None, "generic"),      # non power-of-two T
     (2, 77, 10, 5, "generic"),          # odd T
     (2, 128, 30, None, "generic"),      # D*4 % 16 != 0
-    (1, 512, 768, None, "generic"),     # 2k = T < 1024: sub-transform does not fit
+    (1, 512, 768, None, "fast"),        # wide band: k = 256 = T/2 -> M = 256, R = 2, two band columns per sub-bin (KJ = 16)
+    (3, 512, 384, None, "fast"),        # wide band, KJ = 12 (k = 192)
+    (2, 128, 256, None, "fast"),        # wide band on the 8 x 8 sub-transform: k = 64 = T/2 -> M = 64, R = 2
+    (2, 1024, 1024, None, "fast"),      # k = 512 = T/2 on M = 1024 (not wide: 2k = M), R = 1
+    (2, 2048, 2048, None, "generic"),   # k = 1024: no kernel variant
     (2, 1, 8, 4, "generic"),            # T = 1 -> k = 0: y = bias
     (1, 2, 6, 4, "generic"),            # T = 2 -> k = 1 (DC only)
 ]
