@@ -161,10 +161,10 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+            return float(json.load(open(p))["hbm_gbs"]), "of measured: MEASURED_PEAKS.json hbm_gbs (STREAM-style copy)"
         except Exception:
             pass
-    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+    return 6650.0, "of fallback: 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -360,8 +360,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"SpectralMixingLayer(embed_dim={D}) fwd+bwd, x=({B},{T},{D}) per GPU, {args.dtype} I/O, fp32 math, "
+            "dtype": "f32", "data": "synthetic",      # arithmetic type of the path (bf16 is an I/O type only)
+            "config": {"io_dtype": args.dtype, "workload": f"SpectralMixingLayer(embed_dim={D}) fwd+bwd, x=({B},{T},{D}) per GPU, {args.dtype} I/O, fp32 math, "
                                    f"k={k} live bins, randn x/g/filter, dropout 0 (BASELINE.json configs[1])",
                        "global_batch": world * B, "seq_len": T, "embed_dim": D, "parallelism": f"batch-sharded x{world}",
                        "plan": plan, "l2": f"inputs larger than L2 ({2 * B * T * D * esz / 1e6:.0f} MB read per step vs 126 MB), no flush",
