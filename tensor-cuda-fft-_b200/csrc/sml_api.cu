@@ -126,12 +126,12 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
     const int esz = io_dtype == SML_DTYPE_BF16 ? 2 : 4;
     if ((D * esz) % 16 != 0) return p;   // TMA global strides must be multiples of 16 bytes (and D even)
     // smallest supported square sub-transform M = NR*NR that fits into T and holds the band: M >= 2k (one band column
-    // per sub-bin), or failing that the "wide band" form k <= M of the two small sub-transforms (two band columns per
-    // sub-bin; covers the full half-spectrum cases T = 2k such as T = 512 with embed >= 512 or T = 128)
+    // per sub-bin), or failing that the "wide band" form k <= M (two band columns per sub-bin; covers the full
+    // half-spectrum cases T = 2k such as T = 512 with embed >= 512 or T = 128, and 512 < k <= 1024, i.e. embed up to 2048)
     static const int kNR[3] = {8, 16, 32};
     static const int kP[3] = {32, 8, 4};   // channel pairs per CTA
     for (int pass = 0; pass < 2; ++pass)
-    for (int i = 0; i < (pass == 0 ? 3 : 2); ++i) {
+    for (int i = 0; i < 3; ++i) {
         const int M = kNR[i] * kNR[i];
         if ((pass == 0 ? M >= 2 * p.k : M >= p.k) && M <= T) {
             p.path = SML_PATH_FAST;
@@ -143,10 +143,10 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
             // TMA store address arithmetic and box coordinates stay in 32 bits
             const int need = (p.k + p.NR - 1) / p.NR;   // positive f2 columns that hold live bins
             // instantiated KJ values per NR (see launch_fast)
-            if (p.NR == 32) p.KJ = need <= 8 ? 8 : need <= 12 ? 12 : 16;
+            if (p.NR == 32) p.KJ = need <= 8 ? 8 : need <= 12 ? 12 : need <= 16 ? 16 : need <= 24 ? 24 : 32;
             else if (p.NR == 16) p.KJ = need <= 4 ? 4 : need <= 8 ? 8 : need <= 12 ? 12 : 16;
             else p.KJ = need <= 4 ? 4 : 8;
-            if (p.NR == 32 && p.KJ == 16) p.ctas_per_sm = 2;   // 64 accumulator registers: 3 CTAs/SM would spill
+            if (p.NR == 32 && p.KJ >= 16) p.ctas_per_sm = 2;   // 64+ accumulator registers: 3 CTAs/SM would spill
             if (const char* e = getenv("SML_FAST_CTAS")) {   // tuning knob for the NR=32, KJ=12 kernel: 2 or 3 CTAs per SM
                 if (atoi(e) == 2 && p.NR == 32 && p.KJ == 12) p.ctas_per_sm = 2;
             }
@@ -160,6 +160,7 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
             if (p.NR == 32) {   // M = 1024: warp-specialised kernel, 8 pairs (64-byte TMA rows) per CTA, one CTA per SM
                 p.ws = false;   // experimental (opt-in) until it is parity-green on the GPU
                 if (const char* e = getenv("SML_FAST_WS")) p.ws = atoi(e) != 0;   // tuning knob: 1 = warp-specialised kernel
+                if (p.KJ > 16) p.ws = false;   // the wide band (k > 512) only exists in the lockstep kernel
                 if (p.ws) { p.P = 8; p.ctas_per_sm = 1; }
             }
             return p;

@@ -236,82 +236,88 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
     const int src_lane = (lane & ~(NR - 1)) | ((NR - ff1) & (NR - 1));
     const size_t wrow0 = (size_t)d0 * prm.F, wrow1 = wrow0 + prm.F;
     const size_t xrow0 = ((size_t)b * D + d0) * prm.k, xrow1 = xrow0 + prm.k;
-    // 1. issue every global load of this tile's mid phase up front (filter rows; BWD: saved X_low rows) so that their
-    //    latencies overlap -- the transform registers are dead here, so the values fit
-    float wv[KJ][4];
-    float2 xv[KJ][2];
-#pragma unroll
-    for (int j = 0; j < KJ; ++j) {
-        const int af = ff1 + NR * j;
-        const bool live = pvalid && af < prm.k;
-        wv[j][0] = wv[j][1] = wv[j][2] = wv[j][3] = 0.f;
-        xv[j][0] = xv[j][1] = make_float2(0.f, 0.f);
-        if (live) {
-            wv[j][0] = __ldg(prm.w_re + wrow0 + af);
-            wv[j][1] = __ldg(prm.w_im + wrow0 + af);
-            wv[j][2] = __ldg(prm.w_re + wrow1 + af);
-            wv[j][3] = __ldg(prm.w_im + wrow1 + af);
-            if (grads) {
-                xv[j][0] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
-                xv[j][1] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
-            }
-        }
-    }
-    // 2. each thread filters its KJ non-negative bins and serves the mirror bins of its partner lane
+    // Per chunk of JB bins: 1. issue every global load of the chunk up front (filter rows; BWD: saved X_low rows) so that
+    // their latencies overlap -- the transform registers are dead here, so the values fit; 2. each thread filters its
+    // non-negative bins and serves the mirror bins of its partner lane.
+    constexpr int JB = KJ <= 12 ? KJ : 8;
+    static_assert(KJ % JB == 0, "chunking of the mid phase");
     cf self_mirror = acc[0];   // ff1 == 0: the mirror of bin NR*j is the own bin at index NJ - j (DC mirrors itself)
 #pragma unroll
-    for (int j = 0; j < KJ; ++j) {
-        const int af = ff1 + NR * j;   // fs >= 0
-        const bool live = pvalid && af < prm.k;
-        float mre = __shfl_sync(0xffffffffu, acc[NJ - 1 - j].re, src_lane);
-        float mim = __shfl_sync(0xffffffffu, acc[NJ - 1 - j].im, src_lane);
-        if (ff1 == 0) {
-            mre = self_mirror.re;
-            mim = self_mirror.im;
-        }
-        self_mirror = acc[NJ - 1 - j];   // = acc[NJ - (j + 1)], read before this iteration overwrites it
-        const cf zp = acc[j], zm = cf{mre, mim};
-        // Hermitian split: spectra of the two real channels at +af
-        const cf s0 = cf{0.5f * (zp.re + zm.re), 0.5f * (zp.im - zm.im)};
-        const cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
-        const cf w0 = cf{wv[j][0], wv[j][1]}, w1 = cf{wv[j][2], wv[j][3]};
-        cf a0, a1;
-        if constexpr (!BWD) {
-            if (live && prm.xlow != nullptr) {
-                reinterpret_cast<float2*>(prm.xlow)[xrow0 + af] = make_float2(s0.re, s0.im);
-                reinterpret_cast<float2*>(prm.xlow)[xrow1 + af] = make_float2(s1.re, s1.im);
-            }
-            a0 = cmul(s0, w0);
-            a1 = cmul(s1, w1);
-        } else {
-            if (live && grads) {
-                const cf g0 = cmulc(s0, cf{xv[j][0].x, xv[j][0].y});   // G conj(X)
-                const cf g1 = cmulc(s1, cf{xv[j][1].x, xv[j][1].y});
-                // per-batch-element terms; summed over the batch by filtergrad_reduce_kernel (deterministic, and no
-                // fp32 atomics, which serialise in the LSU at ~1.3 cycles per lane)
-                reinterpret_cast<float2*>(prm.gpart)[xrow0 + af] = make_float2(g0.re * prm.invT, g0.im * prm.invT);
-                reinterpret_cast<float2*>(prm.gpart)[xrow1 + af] = make_float2(g1.re * prm.invT, g1.im * prm.invT);
-                if (af == 0) {
-                    prm.gbpart[(size_t)b * D + d0] = s0.re;
-                    prm.gbpart[(size_t)b * D + d0 + 1] = s1.re;
+    for (int j0 = 0; j0 < KJ; j0 += JB) {
+        float wv[JB][4];
+        float2 xv[JB][2];
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+            const int af = ff1 + NR * (j0 + jj);
+            const bool live = pvalid && af < prm.k;
+            wv[jj][0] = wv[jj][1] = wv[jj][2] = wv[jj][3] = 0.f;
+            xv[jj][0] = xv[jj][1] = make_float2(0.f, 0.f);
+            if (live) {
+                wv[jj][0] = __ldg(prm.w_re + wrow0 + af);
+                wv[jj][1] = __ldg(prm.w_im + wrow0 + af);
+                wv[jj][2] = __ldg(prm.w_re + wrow1 + af);
+                wv[jj][3] = __ldg(prm.w_im + wrow1 + af);
+                if (grads) {
+                    xv[jj][0] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
+                    xv[jj][1] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
                 }
             }
-            a0 = cmulc(s0, w0);   // G conj(W)
-            a1 = cmulc(s1, w1);
         }
-        const float h = 0.5f * prm.invT;
-        cf c = cf{h * (a0.re - a1.im), h * (a0.im + a1.re)};
-        if (af == 0) {   // DC bin; the bias (reference :116) rides on it: a constant in time is a DC term of y_d + i y_{d+1}
-            c = cf{a0.re * prm.invT, a1.re * prm.invT};
-            if constexpr (!BWD) {
-                if (prm.bias != nullptr && pvalid) c = cf{c.re + __ldg(prm.bias + d0), c.im + __ldg(prm.bias + d0 + 1)};
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+            const int j = j0 + jj;
+            const int af = ff1 + NR * j;   // fs >= 0
+            const bool live = pvalid && af < prm.k;
+            float mre = __shfl_sync(0xffffffffu, acc[NJ - 1 - j].re, src_lane);
+            float mim = __shfl_sync(0xffffffffu, acc[NJ - 1 - j].im, src_lane);
+            if (ff1 == 0) {
+                mre = self_mirror.re;
+                mim = self_mirror.im;
             }
+            self_mirror = acc[NJ - 1 - j];   // = acc[NJ - (j + 1)], read before this iteration overwrites it
+            const cf zp = acc[j], zm = cf{mre, mim};
+            // Hermitian split: spectra of the two real channels at +af
+            const cf s0 = cf{0.5f * (zp.re + zm.re), 0.5f * (zp.im - zm.im)};
+            const cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
+            const cf w0 = cf{wv[jj][0], wv[jj][1]}, w1 = cf{wv[jj][2], wv[jj][3]};
+            cf a0, a1;
+            if constexpr (!BWD) {
+                if (live && prm.xlow != nullptr) {
+                    reinterpret_cast<float2*>(prm.xlow)[xrow0 + af] = make_float2(s0.re, s0.im);
+                    reinterpret_cast<float2*>(prm.xlow)[xrow1 + af] = make_float2(s1.re, s1.im);
+                }
+                a0 = cmul(s0, w0);
+                a1 = cmul(s1, w1);
+            } else {
+                if (live && grads) {
+                    const cf g0 = cmulc(s0, cf{xv[jj][0].x, xv[jj][0].y});   // G conj(X)
+                    const cf g1 = cmulc(s1, cf{xv[jj][1].x, xv[jj][1].y});
+                    // per-batch-element terms; summed over the batch by filtergrad_reduce_kernel (deterministic, and no
+                    // fp32 atomics, which serialise in the LSU at ~1.3 cycles per lane)
+                    reinterpret_cast<float2*>(prm.gpart)[xrow0 + af] = make_float2(g0.re * prm.invT, g0.im * prm.invT);
+                    reinterpret_cast<float2*>(prm.gpart)[xrow1 + af] = make_float2(g1.re * prm.invT, g1.im * prm.invT);
+                    if (af == 0) {
+                        prm.gbpart[(size_t)b * D + d0] = s0.re;
+                        prm.gbpart[(size_t)b * D + d0 + 1] = s1.re;
+                    }
+                }
+                a0 = cmulc(s0, w0);   // G conj(W)
+                a1 = cmulc(s1, w1);
+            }
+            const float h = 0.5f * prm.invT;
+            cf c = cf{h * (a0.re - a1.im), h * (a0.im + a1.re)};
+            if (af == 0) {   // DC bin; the bias (reference :116) rides on it: a constant in time is a DC term of y_d + i y_{d+1}
+                c = cf{a0.re * prm.invT, a1.re * prm.invT};
+                if constexpr (!BWD) {
+                    if (prm.bias != nullptr && pvalid) c = cf{c.re + __ldg(prm.bias + d0), c.im + __ldg(prm.bias + d0 + 1)};
+                }
+            }
+            acc[j] = c;
+            // hand the value for the mirror bin -fs to its owner (the partner does the same for this thread)
+            const cf cn = cf{h * (a0.re + a1.im), h * (a1.re - a0.im)};
+            acc[NJ - 1 - j].re = __shfl_sync(0xffffffffu, cn.re, src_lane);
+            acc[NJ - 1 - j].im = __shfl_sync(0xffffffffu, cn.im, src_lane);
         }
-        acc[j] = c;
-        // hand the value for the mirror bin -fs to its owner (the partner does the same for this thread)
-        const cf cn = cf{h * (a0.re + a1.im), h * (a1.re - a0.im)};
-        acc[NJ - 1 - j].re = __shfl_sync(0xffffffffu, cn.re, src_lane);
-        acc[NJ - 1 - j].im = __shfl_sync(0xffffffffu, cn.im, src_lane);
     }
     // ff1 == 0 lanes received their own values one index too low (bin -NR*j belongs at NJ - j); index KJ is the bin
     // -NR*KJ, outside the band

@@ -74,6 +74,8 @@ int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map
     SML_CASE(32, 8, 4, 3)
     SML_CASE(32, 12, 4, 3)
     SML_CASE(32, 16, 4, 2)
+    SML_CASE(32, 24, 4, 2)
+    SML_CASE(32, 32, 4, 2)
     SML_CASE(32, 12, 4, 2)
     SML_CASE(16, 4, 8, 3)
     SML_CASE(16, 8, 8, 3)

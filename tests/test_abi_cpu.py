@@ -46,7 +46,9 @@ def test_plan_selection(native):
     assert native.plan(4, 512, 768, 384) == {"path": "fast", "M": 256, "R": 2, "k": 256}
     assert native.plan(2, 128, 256, 128) == {"path": "fast", "M": 64, "R": 2, "k": 64}
     assert native.plan(2, 512, 384, 192) == {"path": "fast", "M": 256, "R": 2, "k": 192}
-    assert native.plan(2, 2048, 2048, 1024)["path"] == "generic"   # k = 1024 > 512: no kernel variant
+    assert native.plan(2, 2048, 2048, 1024) == {"path": "fast", "M": 1024, "R": 2, "k": 1024}   # embed 2048
+    assert native.plan(2, 8192, 1536, 768) == {"path": "fast", "M": 1024, "R": 8, "k": 768}
+    assert native.plan(2, 4096, 4096, 2048)["path"] == "generic"   # k = 2048 > 1024: no kernel variant
     assert native.plan(16, 8192, 768, 384, native.DTYPE_BF16)["path"] == "fast"
 
 

@@ -99,7 +99,8 @@ SHAPES = [
     (3, 512, 384, None, "fast"),        # wide band, KJ = 12 (k = 192)
     (2, 128, 256, None, "fast"),        # wide band on the 8 x 8 sub-transform: k = 64 = T/2 -> M = 64, R = 2
     (2, 1024, 1024, None, "fast"),      # k = 512 = T/2 on M = 1024 (not wide: 2k = M), R = 1
-    (2, 2048, 2048, None, "generic"),   # k = 1024: no kernel variant
+    (1, 2048, 2048, None, "fast"),      # wide band on M = 1024: k = 1024 = T/2 (KJ = 32), embed 2048
+    (1, 4096, 1536, None, "fast"),      # wide band on M = 1024: k = 768 (KJ = 24), R = 4
     (2, 1, 8, 4, "generic"),            # T = 1 -> k = 0: y = bias
     (1, 2, 6, 4, "generic"),            # T = 2 -> k = 1 (DC only)
 ]
