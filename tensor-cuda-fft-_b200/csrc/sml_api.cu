@@ -344,7 +344,8 @@ __global__ void accumulate_kernel(float* __restrict__ total, const float* __rest
 struct HostPipe {
     static constexpr int NBUF = 3;
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[NBUF] = {}, ev_cmp[NBUF] = {}, ev_out[NBUF] = {};
+    cudaEvent_t ev_in[NBUF] = {}, ev_cmp[NBUF] = {}, ev_out[NBUF] = {};   // g landed, kernels done, gx left
+    cudaEvent_t ev_x[NBUF] = {}, ev_fwd[NBUF] = {};                       // x landed, forward done
     char* act[NBUF][4] = {};   // x, g, y, gx
     char* xlow[NBUF] = {};
     char* ws[NBUF] = {};
@@ -366,6 +367,8 @@ int pipe_reserve(HostPipe& hp, size_t act_bytes, size_t xlow_bytes, size_t ws_by
             SML_CUDA(cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming));
             SML_CUDA(cudaEventCreateWithFlags(&hp.ev_cmp[i], cudaEventDisableTiming));
             SML_CUDA(cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming));
+            SML_CUDA(cudaEventCreateWithFlags(&hp.ev_x[i], cudaEventDisableTiming));
+            SML_CUDA(cudaEventCreateWithFlags(&hp.ev_fwd[i], cudaEventDisableTiming));
         }
         hp.ready = true;
     }
@@ -442,17 +445,24 @@ int fwd_bwd_host_impl(const void* x, const void* g, const float* w_re, const flo
         const int b0 = i * cb, nb = (B - b0 < cb) ? B - b0 : cb;
         const size_t off = (size_t)b0 * row_bytes, bytes = (size_t)nb * row_bytes;
         char *dx = hp.act[s][0], *dg = hp.act[s][1], *dy = hp.act[s][2], *dgx = hp.act[s][3];
-        // H2D: the slot's x/g are free once the kernels of chunk i - NBUF have run
+        // H2D: the slot's x/g are free once the kernels of chunk i - NBUF have run.  x and g get their own events so the
+        // forward starts as soon as x is in, and y leaves while the backward still runs (shorter pipeline fill and drain).
         if (i >= HostPipe::NBUF) SML_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_cmp[s], 0));
         SML_CUDA(cudaMemcpyAsync(dx, (const char*)x + off, bytes, cudaMemcpyHostToDevice, hp.s_in));
+        SML_CUDA(cudaEventRecord(hp.ev_x[s], hp.s_in));
         SML_CUDA(cudaMemcpyAsync(dg, (const char*)g + off, bytes, cudaMemcpyHostToDevice, hp.s_in));
         SML_CUDA(cudaEventRecord(hp.ev_in[s], hp.s_in));
-        // kernels: wait for the inputs and for the slot's y/gx to have left (D2H of chunk i - NBUF)
-        SML_CUDA(cudaStreamWaitEvent(hp.s_cmp, hp.ev_in[s], 0));
+        // forward: wait for x and for the slot's y/gx to have left (D2H of chunk i - NBUF)
+        SML_CUDA(cudaStreamWaitEvent(hp.s_cmp, hp.ev_x[s], 0));
         if (i >= HostPipe::NBUF) SML_CUDA(cudaStreamWaitEvent(hp.s_cmp, hp.ev_out[s], 0));
         if (forward_impl<IO>(dx, d_wre, d_wim, d_bias, dy, want_grads || hp.cap_ws ? hp.xlow[s] : nullptr, nb, T, D, F,
                              io_dtype, hp.s_cmp))
             return 1;
+        SML_CUDA(cudaEventRecord(hp.ev_fwd[s], hp.s_cmp));
+        SML_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_fwd[s], 0));
+        SML_CUDA(cudaMemcpyAsync((char*)y + off, dy, bytes, cudaMemcpyDeviceToHost, hp.s_out));
+        // backward: wait for g
+        SML_CUDA(cudaStreamWaitEvent(hp.s_cmp, hp.ev_in[s], 0));
         float* pg = want_grads ? hp.grad_part : nullptr;
         if (backward_impl<IO>(dg, want_grads ? hp.xlow[s] : nullptr, d_wre, d_wim, dgx, pg, pg ? pg + nW : nullptr,
                               pg ? pg + 2 * nW : nullptr, hp.ws[s], hp.cap_ws, nb, T, D, F, io_dtype, hp.s_cmp))
@@ -462,9 +472,7 @@ int fwd_bwd_host_impl(const void* x, const void* g, const float* w_re, const flo
             count_launch();
         }
         SML_CUDA(cudaEventRecord(hp.ev_cmp[s], hp.s_cmp));
-        // D2H
         SML_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_cmp[s], 0));
-        SML_CUDA(cudaMemcpyAsync((char*)y + off, dy, bytes, cudaMemcpyDeviceToHost, hp.s_out));
         SML_CUDA(cudaMemcpyAsync((char*)gx + off, dgx, bytes, cudaMemcpyDeviceToHost, hp.s_out));
         SML_CUDA(cudaEventRecord(hp.ev_out[s], hp.s_out));
     }

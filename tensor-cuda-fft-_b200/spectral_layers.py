@@ -42,6 +42,28 @@ def _stream_handle(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _on_device:
+    """``torch.cuda.device(dev)`` only when dev is not already current (the context manager costs ~15 us per use,
+    which is most of a forward call at small shapes)."""
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.contiguous().float()
+
+
 class _SpectralMixFn(torch.autograd.Function):
     """y = Re(ifft(lowpass(fft(x) * W))) + bias, with the backward of spectral_layers.py:88-116
     (== WirtingerGradient.backward, wirtinger_ops.py:53-82) computed by sml_backward."""
@@ -59,16 +81,15 @@ class _SpectralMixFn(torch.autograd.Function):
         io = _IO_DTYPES[x.dtype]
         lib = _native.lib()
         xc = x.contiguous()
-        wr = w_re.detach().contiguous().float()
-        wi = w_im.detach().contiguous().float()
-        bs = None if bias is None else bias.detach().contiguous().float()
+        wr, wi = _f32c(w_re), _f32c(w_im)
+        bs = None if bias is None else _f32c(bias)
         y = torch.empty_like(xc)
         need_filter_grad = any(ctx.needs_input_grad[1:])
         fast_path, nbytes, _ = _shape_info(B, T, D, Fn, io)
         xlow = None
         if need_filter_grad or not fast_path:
             xlow = torch.empty(max(nbytes // 8, 1), dtype=torch.complex64, device=x.device)
-        with torch.cuda.device(x.device):
+        with _on_device(x.device):
             _native.check(lib.sml_forward(_ptr(xc), _ptr(wr), _ptr(wi), _ptr(bs), _ptr(y), _ptr(xlow),
                                           B, T, D, Fn, io, _stream_handle(x.device)))
         ctx.save_for_backward(wr, wi, xlow if need_filter_grad else None)
@@ -99,7 +120,7 @@ class _SpectralMixFn(torch.autograd.Function):
         # fast path: scratch only for the filter-gradient terms; generic path: always (low-band spectrum of g)
         ws_bytes = _shape_info(B, T, D, Fn, io)[2] if (want or not ctx.fast_path) else 0
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gc.device) if ws_bytes else None
-        with torch.cuda.device(gc.device):
+        with _on_device(gc.device):
             _native.check(lib.sml_backward(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gx), _ptr(gwr), _ptr(gwi),
                                            _ptr(gb), _ptr(ws), ws_bytes, B, T, D, Fn, io, _stream_handle(gc.device)))
         need = ctx.needs_input_grad
@@ -187,6 +208,8 @@ class SpectralMixingLayer(nn.Module):
             if not x.is_cuda:
                 raise RuntimeError("SpectralMixingLayer (B200 build) needs a CUDA tensor; there is no CPU path")
             y = x.clone()
+        if self.dropout.p == 0.0 or not self.training:     # nn.Dropout is the identity here: skip the call
+            return y
         return self.dropout(y)
 
     def verify_energy_preservation(self, x: torch.Tensor, y: torch.Tensor) -> float:
