@@ -42,6 +42,43 @@ def _fft_backend():
     return "MKL DFTI" if torch.backends.mkl.is_available() else "pocketfft"
 
 
+def _cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown CPU"
+
+
+def gpu_reference_algorithm(x, g, w_re, w_im, bias, steps=5):
+    """Context only: the reference ALGORITHM (fft_tensor/spectral_layers.py:88-116: torch.fft.fft, complex filter into a zero
+    tensor, torch.fft.ifft(...).real, + bias; autograd backward) executed by PyTorch/cuFFT on the same GPU and inputs."""
+    params = [p.detach().clone().requires_grad_(True) for p in (w_re, w_im, bias)]
+
+    def step():
+        for p in params:
+            p.grad = None
+        xr = x.detach().float().requires_grad_(True)
+        spec = torch.fft.fft(xr, dim=1)
+        k = min(params[0].shape[1], xr.shape[1] // 2)
+        kept = torch.zeros_like(spec)
+        kept[:, :k, :] = spec[:, :k, :] * torch.complex(params[0], params[1])[:, :k].T.unsqueeze(0)
+        (torch.fft.ifft(kept, dim=1).real + params[2]).backward(g.float())
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -96,7 +133,7 @@ def run_reference_arm(args):
         "config": {"workload": f"SpectralMixingLayer(embed_dim={D}) fwd+bwd, x=({args.batch},{T},{D}) fp32, k={min(D // 2, T // 2)}",
                    "note": f"CPU arm: each step is a bounded sample of the workload, batch {B} of {args.batch} (columns are independent)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"oracle torch port (torch.fft, {_fft_backend()}), "
+                         "sample": f"oracle torch port (torch.fft, {_fft_backend()}, {_cpu_model()}), "
                                    f"x=({B},{T},{D}) fwd+bwd, mean of {n} steps"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -352,9 +389,19 @@ def run_ours(args):
         Bs = min(args.cpu_sample_batch, B)
         dt, n, threads = cpu_reference_step_time(Bs, T, D, steps=40, warmup=1, budget_s=12.0)
         cpu = {"value": Bs * T / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"oracle torch port (torch.fft on host, {_fft_backend()}), "
+               "sample": f"oracle torch port (torch.fft on host, {_fft_backend()}, {_cpu_model()}), "
                          f"x=({Bs},{T},{D}) fp32 fwd+bwd (batch {Bs} of {B}; columns independent), mean of {n} steps",
                "ms_per_step": dt * 1e3}
+
+    # ---- context: the reference algorithm through PyTorch/cuFFT on this same GPU (rank 0, N=1 only) ----
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            ms_ref = gpu_reference_algorithm(x, g, wr, wi, bs)
+            gpu_ref = {"value": B * T / (ms_ref * 1e-3), "unit": UNIT, "ms_per_step": ms_ref,
+                       "what": "reference algorithm (torch.fft/cuFFT + ATen elementwise + autograd, fp32) on the same B200 and shape; context, not an arm"}
+        except Exception as e:   # e.g. out of memory at very large shapes: context only
+            gpu_ref = {"unavailable": str(e).splitlines()[0][:200]}
 
     if rank == 0:
         line = {
@@ -369,7 +416,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_step": roofline_step,
-            "e2e": e2e, "cpu_baseline": cpu,
+            "e2e": e2e, "cpu_baseline": cpu, "reference_algorithm_on_gpu": gpu_ref,
         }
         print_line(json.dumps(line))
     if world > 1:

@@ -76,6 +76,10 @@ class _SpectralMixFn(torch.autograd.Function):
             raise RuntimeError(f"Unsupported dtype {x.dtype}")   # reference raises on bf16; here fp32 and bf16 are I/O types
         if x.dim() != 3:
             raise RuntimeError(f"expected (B, T, D) input, got shape {tuple(x.shape)}")
+        if w_re.device != x.device or w_im.device != x.device or (bias is not None and bias.device != x.device):
+            raise RuntimeError(f"input is on {x.device} but the filter parameters are on {w_re.device}")
+        if w_re.shape != w_im.shape or w_re.dim() != 2 or w_re.shape[0] != x.shape[2]:
+            raise RuntimeError(f"filter shape {tuple(w_re.shape)} / {tuple(w_im.shape)} does not match embed dim {x.shape[2]}")
         B, T, D = x.shape
         Fn = w_re.shape[1]
         io = _IO_DTYPES[x.dtype]

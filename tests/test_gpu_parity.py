@@ -378,6 +378,21 @@ def test_language_model_golden(pkg, dev, golden_dir):
     assert text.startswith("ab") and len(text) >= 3
 
 
+def test_errors_are_loud(pkg, dev):
+    # no silent fallback: wrong device, wrong dtype, wrong rank and mismatched filters raise
+    layer = pkg.SpectralMixingLayer(32).to(dev)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        pkg.SpectralMixingLayer(32)(torch.randn(2, 64, 32))                       # CPU tensor, CPU module
+    with pytest.raises(RuntimeError, match="Unsupported dtype"):
+        layer(torch.randn(2, 64, 32, device=dev, dtype=torch.float16))
+    with pytest.raises(AssertionError, match="Expected embed_dim=32, got 16"):      # reference message, spectral_layers.py:84
+        layer(torch.randn(2, 64, 16, device=dev))
+    with pytest.raises(RuntimeError, match="filter parameters are on"):
+        pkg.SpectralMixingLayer(32)(torch.randn(2, 64, 32, device=dev))           # CPU module, CUDA tensor
+    with pytest.raises(RuntimeError, match="does not match embed dim"):
+        pkg.spectral_mix(torch.randn(2, 64, 32, device=dev), torch.randn(16, 8, device=dev), torch.randn(16, 8, device=dev))
+
+
 def test_cuda_graph_capture(pkg, dev):
     # forward + backward of the layer captured once in a CUDA graph and replayed on new data (no host work per replay):
     # the library calls are capture-safe after one warm-up (twiddle table built, contexts bound)
