@@ -23,7 +23,6 @@ import json
 import os
 import statistics
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -82,7 +81,7 @@ def gpu_reference_algorithm(x, g, w_re, w_im, bias, steps=5):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
@@ -144,49 +143,64 @@ def run_reference_arm(args):
 # clocks sampler (nvidia-smi fields through NVML)
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
-               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
-               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+    """SM clock and throttle reasons DURING the timed region.  A separate `nvidia-smi -lms` process does the sampling (a
+    Python thread in this process is starved of the GIL by the launch loop); samples are kept if their timestamp falls
+    inside [mark_begin, mark_end]."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, index):
-        self.samples, self.reasons, self.ok = [], set(), False
-        self._stop = threading.Event()
+    def __init__(self, index, interval_ms=10):
+        import subprocess
+        import tempfile
+        self.proc, self.t0, self.t1 = None, None, None
+        self.out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", str(interval_ms)], stdout=self.out, stderr=subprocess.DEVNULL)
         except Exception as e:   # pragma: no cover
             self.err = str(e)
-        self.t = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit and name != "gpu_idle":
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop.wait(0.002)
+    def start(self):      # kept for symmetry: the process is already running (its start-up takes ~0.1 s)
+        pass
 
-    def start(self):
-        if self.ok:
-            self.t.start()
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        self._stop.set()
-        if self.ok and self.t.is_alive():
-            self.t.join(timeout=2)
-        if not self.ok or not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        import datetime
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi_unavailable"]}
+        time.sleep(0.03)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        self.out.flush()
+        rows = []
+        for ln in open(self.out.name):
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[4:8]))
+            except Exception:
+                continue
+        try:
+            os.unlink(self.out.name)
+        except OSError:
+            pass
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.005 <= r[0] <= self.t1 + 0.005] or rows[-3:]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no_samples"]}
+        reasons = sorted({n for r in inside for n, v in zip(self.NAMES, r[4]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": inside[0][2], "reasons": reasons,
+                "samples": len(inside), "power_w_max": max(r[3] for r in inside), "sampler": "nvidia-smi -lms 10, samples inside the timed region"}
 
 
 def _collective_path():
@@ -255,21 +269,22 @@ def run_ours(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)      # separate process; started before the warm-up so it is sampling by the time we measure
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
 
     # ---- timed region: exactly K steps, CUDA events, max over ranks ----
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = _native.launch_count()
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = _native.launch_count() - n0
     ms_total = e0.elapsed_time(e1)

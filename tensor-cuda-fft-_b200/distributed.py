@@ -121,10 +121,15 @@ def allreduce_filter_grads(modules: Iterable[torch.nn.Module], group: Optional[d
     if flat.is_cuda and not async_op and flat.dtype == torch.float32 and use_symm:
         symm = _SymmetricAllReduce.get(flat.numel(), flat.device, group if group is not None else dist.group.WORLD)
     global LAST_ALLREDUCE_PATH
+    done = False
     if symm is not None and symm.ok:
-        symm(flat)                      # NVLink/NVSwitch symmetric-memory reduction (NVLS multimem when available)
-        LAST_ALLREDUCE_PATH = "symm_mem multimem" if symm.multicast else "symm_mem one_shot"
-    else:
+        try:
+            symm(flat)                  # NVLink/NVSwitch symmetric-memory reduction (NVLS multimem when available)
+            LAST_ALLREDUCE_PATH = "symm_mem multimem" if symm.multicast else "symm_mem one_shot"
+            done = True
+        except Exception as e:          # pragma: no cover - e.g. an op missing from this torch build: use NCCL from now on
+            symm.ok, symm.err = False, repr(e)
+    if not done:
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         LAST_ALLREDUCE_PATH = "nccl"
 
