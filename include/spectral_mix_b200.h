@@ -28,7 +28,7 @@ extern "C" {
 #define SML_DTYPE_F32 0
 #define SML_DTYPE_BF16 1
 
-#define SML_PATH_FAST 1    /* fused streamed band-limited FFT kernel (power-of-two T) */
+#define SML_PATH_FAST 1    /* fused streamed band-limited FFT kernel (T a multiple of the sub-transform length M) */
 #define SML_PATH_GENERIC 2 /* direct band-limited DFT kernels (any T, D, F) */
 
 /* ABI version of this header (bumped on any signature change). */

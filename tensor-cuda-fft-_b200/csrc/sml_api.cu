@@ -117,15 +117,14 @@ int twiddle_table(DeviceState* st, int T, cudaStream_t stream, const sml::cf** o
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 Plan make_plan(int T, int D, int F, int io_dtype) {
     Plan p;
     p.k = F < T / 2 ? F : T / 2;
-    if (p.k < 1 || !is_pow2(T)) return p;
+    if (p.k < 1) return p;
     const int esz = io_dtype == SML_DTYPE_BF16 ? 2 : 4;
     if ((D * esz) % 16 != 0) return p;   // TMA global strides must be multiples of 16 bytes (and D even)
-    // smallest supported square sub-transform M = NR*NR that fits into T and holds the band: M >= 2k (one band column
+    // smallest supported square sub-transform M = NR*NR that divides T and holds the band: M >= 2k (one band column
     // per sub-bin), or failing that the "wide band" form k <= M (two band columns per sub-bin; covers the full
     // half-spectrum cases T = 2k such as T = 512 with embed >= 512 or T = 128, and 512 < k <= 1024, i.e. embed up to 2048)
     static const int kNR[3] = {8, 16, 32};
@@ -133,7 +132,7 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
     for (int pass = 0; pass < 2; ++pass)
     for (int i = 0; i < 3; ++i) {
         const int M = kNR[i] * kNR[i];
-        if ((pass == 0 ? M >= 2 * p.k : M >= p.k) && M <= T) {
+        if ((pass == 0 ? M >= 2 * p.k : M >= p.k) && M <= T && T % M == 0) {   // any T = R * M, R need not be a power of two
             p.path = SML_PATH_FAST;
             p.NR = kNR[i];
             p.P = kP[i];
@@ -232,7 +231,7 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
         if (encode_act_map(&map, x, B, T, D, io_dtype, p)) return 1;
         if (encode_act_map(&map_out, y, B, T, D, io_dtype, p)) return 1;
         sml::FastParams prm{};
-        prm.in = x; prm.out = y; prm.w_re = w_re; prm.w_im = w_im; prm.bias = bias;
+        prm.out = y; prm.w_re = w_re; prm.w_im = w_im; prm.bias = bias;
         prm.xlow = reinterpret_cast<sml::cf*>(xlow);
         prm.gtab = gtab;
         prm.B = B; prm.T = T; prm.D = D; prm.F = F; prm.k = p.k; prm.R = p.R;
@@ -284,7 +283,7 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         if (encode_act_map(&map, g, B, T, D, io_dtype, p)) return 1;
         if (encode_act_map(&map_out, gx, B, T, D, io_dtype, p)) return 1;
         sml::FastParams prm{};
-        prm.in = g; prm.out = gx; prm.w_re = w_re; prm.w_im = w_im; prm.bias = nullptr;
+        prm.out = gx; prm.w_re = w_re; prm.w_im = w_im; prm.bias = nullptr;
         prm.xlow = reinterpret_cast<sml::cf*>(const_cast<void*>(xlow));
         prm.gw_re = gw_re;
         prm.gpart = want_grads ? reinterpret_cast<sml::cf*>(ws) : nullptr;

@@ -1,4 +1,4 @@
-// sml_fast.cuh -- fused SpectralMixingLayer forward / backward kernels for sm_100a (power-of-two T).
+// sml_fast.cuh -- fused SpectralMixingLayer forward / backward kernels for sm_100a (T = R * M, M in {64, 256, 1024}).
 //
 // What one launch computes (reference: /root/reference/fft_tensor/spectral_layers.py:88-116 and the
 // autograd graph it implies, == /root/reference/fft_tensor/wirtinger_ops.py:53-82):
@@ -38,7 +38,6 @@
 namespace sml {
 
 struct FastParams {
-    const void* in;        // x (FWD) or g (BWD): (B,T,D) IO -- used by the cp.async load path
     void* out;             // y (FWD) or gx (BWD): (B,T,D) IO
     const float* w_re;     // (D,F)
     const float* w_im;     // (D,F)
@@ -394,7 +393,9 @@ __global__ void __launch_bounds__(NR* P, MINB)
     // uniform twiddle of pass r for band column j = tid (threads < NJ): W_T^{NR r f2s}, f2s = j (j < KJ) or j - NJ
     auto cj_load = [&](int r) -> float2 {
         const int f2s = tid < KJ ? tid : tid - NJ;
-        return __ldg(gtab + ((NR * r * f2s) & (T - 1)));
+        int idx = (NR * r * f2s) % T;   // T = R * M need not be a power of two
+        if (idx < 0) idx += T;
+        return __ldg(gtab + idx);
     };
 
     if (tid == 0) {
@@ -542,8 +543,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
 }
 
 // batch reduction of the filter / bias gradient terms written by the BWD kernel (wirtinger_ops.py:77-80: sum over dim 0).
-// One thread per (d, pair of bins f, f+1 < F) -- k is even on the fast path (k = min(F, T/2) with T a power of two and
-// 2k <= M, or k = F handled by the scalar tail); also zero-fills the columns f >= k, so no memset is needed.
+// One thread per (d, pair of bins f, f+1 < F) -- pairs that are not both live or not 16-byte aligned take the scalar tail; also zero-fills the columns f >= k, so no memset is needed.
 // Deterministic (fixed summation order over b).
 static __global__ void filtergrad_reduce_kernel(const float2* __restrict__ gpart, const float* __restrict__ gbpart,
                                                 float* __restrict__ gw_re, float* __restrict__ gw_im,

@@ -203,7 +203,9 @@ __global__ void __launch_bounds__(512, 1)
         cf* const cjs = cjbuf + fp2 * NR;         // this warp's private twiddle slot
         auto cj_load = [&](int r) -> float2 {     // lane f2: W_T^{NR r f2s}
             const int f2s = ff1 < NR / 2 ? ff1 : ff1 - NR;
-            return __ldg(gtab + ((NR * r * f2s) & (T - 1)));
+            int idx = (NR * r * f2s) % T;   // T = R * M need not be a power of two
+        if (idx < 0) idx += T;
+        return __ldg(gtab + idx);
         };
         unsigned int c = 0;
         for (int it = 0; it < my_ntiles; ++it) {

@@ -1,5 +1,5 @@
 // sml_generic.cuh -- direct band-limited DFT kernels: correct for ANY (T, D, F), used when the fused fast
-// path does not apply (non power-of-two T, odd D, very wide filter banks).  Still CUDA-only: there is no
+// path does not apply (T not a multiple of the sub-transform length, odd D, very wide filter banks).  Still CUDA-only: there is no
 // CPU fallback anywhere in the library.
 //
 //   analysis  : X[b,d,f] = sum_t x[b,t,d] W_T^{f t}                      f < k   (spectral_layers.py:88, :101)

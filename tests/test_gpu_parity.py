@@ -92,7 +92,11 @@ SHAPES = [
     (1, 2048, 40, 200, "fast"),         # D not a multiple of the channel tile, KJ=8 variant
     (2, 1024, 36, 300, "fast"),         # D % 16 = 4
     (1, 8192, 32, 384, "fast"),         # cfg-2 column geometry: M=1024, R=8
-    (2, 384, 48, None, "generic"),      # non power-of-two T
+    (2, 384, 48, None, "fast"),         # T = 6 * 64: not a power of two, still a multiple of the sub-transform
+    (1, 3072, 768, None, "fast"),       # T = 3 * 1024 at the cfg-2 band
+    (2, 1536, 96, None, "fast"),        # T = 6 * 256
+    (1, 5120, 64, 512, "fast"),         # T = 5 * 1024, k = 512
+    (2, 1000, 40, None, "generic"),     # T not a multiple of 64
     (2, 77, 10, 5, "generic"),          # odd T
     (2, 128, 30, None, "generic"),      # D*4 % 16 != 0
     (1, 512, 768, None, "fast"),        # wide band: k = 256 = T/2 -> M = 256, R = 2, two band columns per sub-bin (KJ = 16)
