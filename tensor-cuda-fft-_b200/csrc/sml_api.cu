@@ -246,12 +246,12 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
     // generic path
     if (p.k > 0 && xlow == nullptr) return fail("generic path needs the xlow buffer (sml_xlow_bytes) as scratch");
     if (p.k > 0) {
-        dim3 blk(32, 8), ga((D + 31) / 32, (p.k + 7) / 8, B), gs((D + 31) / 32, (T + 7) / 8, B);
+        dim3 blk(256), ga((D + 63) / 64, (p.k + 63) / 64, B), gs((D + 63) / 64, (T + 63) / 64, B);
         sml::generic_analysis_kernel<IO><<<ga, blk, 0, stream>>>((const IO*)x, (sml::cf*)xlow, gtab, T, D, p.k);
         sml::generic_synthesis_kernel<IO, false><<<gs, blk, 0, stream>>>((const sml::cf*)xlow, w_re, w_im, bias, (IO*)y, gtab, T, D, F, p.k, invT);
         count_launch(2);
     } else {
-        dim3 blk(32, 8), gs((D + 31) / 32, (T + 7) / 8, B);
+        dim3 blk(256), gs((D + 63) / 64, (T + 63) / 64, B);
         sml::generic_synthesis_kernel<IO, false><<<gs, blk, 0, stream>>>(nullptr, w_re, w_im, bias, (IO*)y, gtab, T, D, F, 0, invT);
         count_launch();
     }
@@ -309,9 +309,9 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
     // generic path: G into workspace, then synthesis with conj(W) and the batch reduction
     const size_t need = sizeof(sml::cf) * (size_t)B * D * (size_t)p.k;
     if (p.k > 0 && (ws == nullptr || ws_bytes < need)) return fail("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
-    dim3 blk(32, 8), gs((D + 31) / 32, (T + 7) / 8, B);
+    dim3 blk(256), gs((D + 63) / 64, (T + 63) / 64, B);
     if (p.k > 0) {
-        dim3 ga((D + 31) / 32, (p.k + 7) / 8, B);
+        dim3 ga((D + 63) / 64, (p.k + 63) / 64, B);
         sml::generic_analysis_kernel<IO><<<ga, blk, 0, stream>>>((const IO*)g, (sml::cf*)ws, gtab, T, D, p.k);
         count_launch();
     }
