@@ -129,10 +129,11 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
     // half-spectrum cases T = 2k such as T = 512 with embed >= 512 or T = 128, and 512 < k <= 1024, i.e. embed up to 2048)
     static const int kNR[3] = {8, 16, 32};
     static const int kP[3] = {32, 8, 4};   // channel pairs per CTA
-    for (int pass = 0; pass < 2; ++pass)
-    for (int i = 0; i < 3; ++i) {
+    // pass 0: one band bin per sub-bin (M >= 2k); pass 1: two (M >= k); pass 2: up to four (2M >= k), small sub-transforms only
+    for (int pass = 0; pass < 3; ++pass)
+    for (int i = 0; i < (pass == 2 ? 2 : 3); ++i) {
         const int M = kNR[i] * kNR[i];
-        if ((pass == 0 ? M >= 2 * p.k : M >= p.k) && M <= T && T % M == 0) {   // any T = R * M, R need not be a power of two
+        if ((pass == 0 ? M >= 2 * p.k : pass == 1 ? M >= p.k : 2 * M >= p.k) && M <= T && T % M == 0) {   // any T = R * M
             p.path = SML_PATH_FAST;
             p.NR = kNR[i];
             p.P = kP[i];
@@ -143,8 +144,9 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
             const int need = (p.k + p.NR - 1) / p.NR;   // positive f2 columns that hold live bins
             // instantiated KJ values per NR (see launch_fast)
             if (p.NR == 32) p.KJ = need <= 8 ? 8 : need <= 12 ? 12 : need <= 16 ? 16 : need <= 24 ? 24 : 32;
-            else if (p.NR == 16) p.KJ = need <= 4 ? 4 : need <= 8 ? 8 : need <= 12 ? 12 : 16;
-            else p.KJ = need <= 4 ? 4 : 8;
+            else if (p.NR == 16) p.KJ = need <= 4 ? 4 : need <= 8 ? 8 : need <= 12 ? 12 : need <= 16 ? 16 : need <= 24 ? 24 : 32;
+            else p.KJ = need <= 4 ? 4 : need <= 8 ? 8 : 16;
+            if (p.NR == 16 && p.KJ == 32) p.ctas_per_sm = 2;   // 128 accumulator registers
             if (p.NR == 32 && p.KJ >= 16) p.ctas_per_sm = 2;   // 64+ accumulator registers: 3 CTAs/SM would spill
             if (const char* e = getenv("SML_FAST_CTAS")) {   // tuning knob for the NR=32, KJ=12 kernel: 2 or 3 CTAs per SM
                 if (atoi(e) == 2 && p.NR == 32 && p.KJ == 12) p.ctas_per_sm = 2;

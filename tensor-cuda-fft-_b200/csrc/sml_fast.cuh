@@ -162,7 +162,7 @@ struct FastCfg {
     static constexpr int NT = NR * P;
     static constexpr int M = NR * NR;
     static constexpr int XS = NR + 2;    // exchange row stride (complex): rows stay 16-byte aligned (128-bit row access)
-    static constexpr int CJN = 2 * NR;   // pass twiddles per slot: one per band column (up to 2 NR columns, see KJ)
+    static constexpr int CJN = 4 * NR;   // pass twiddles per slot: one per band column (up to 4 NR columns, see KJ)
     static constexpr int BOXROWS = M < 256 ? M : 256;
     static constexpr int NBOX = M / BOXROWS;
     static constexpr uint32_t LOAD_BYTES = (uint32_t)M * 2u * P * sizeof(IO);            // X: one TMA stage, dense [M][2P]
@@ -327,6 +327,20 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
     }
 }
 
+// band column j -> sub-bin column f2 (the signed column index f2s = j or j - NJ, wrapped into [0, NR))
+template <int NR, int KJ>
+__host__ __device__ constexpr int band_f2(int j) {
+    const int f2s = j < KJ ? j : j - 2 * KJ;
+    return ((f2s % NR) + NR) % NR;
+}
+// true if no earlier band column lands on the same sub-bin column (synthesis: assign instead of accumulate)
+template <int NR, int KJ>
+__host__ __device__ constexpr bool band_first(int j) {
+    for (int jj = 0; jj < j; ++jj)
+        if (band_f2<NR, KJ>(jj) == band_f2<NR, KJ>(j)) return false;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -349,7 +363,9 @@ __global__ void __launch_bounds__(NR* P, MINB)
     // column.  NR/2 < KJ <= NR ("wide band", k <= M): a sub-bin f1 + NR f2 carries two band bins, fs = f1 + NR f2 >= 0 and
     // fs - M < 0, i.e. columns j = f2 and j = f2 + NJ - NR accumulate the same DFT output with different pass twiddles --
     // this is what lets T = 2k (full half-spectrum, e.g. T = 512 with embed >= 512) run with M = T/2, R = 2.
-    static_assert(NJ <= 2 * NR, "band wider than two periods of the sub-transform");
+    // In general a sub-bin carries ceil(NJ / NR) band bins ("aliases", fs = f1 + NR f2 + q M): up to four periods are
+    // instantiated for the two small sub-transforms, which keeps T = R * 256 fused for bands up to k = 512.
+    static_assert(NJ <= 4 * NR, "band wider than four periods of the sub-transform");
     static_assert(NT % 32 == 0 && 32 % NR == 0, "freq-side partner bin must live in the same warp");
     constexpr int CJN = C::CJN;
 
@@ -470,10 +486,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
             {
                 const cf* cjs = cj + slot * CJN;
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const int f2 = j < KJ ? j : NR - NJ + j;
-                    acc[j] = cmac(acc[j], v[f2], cjs[j]);
-                }
+                for (int j = 0; j < NJ; ++j) acc[j] = cmac(acc[j], v[band_f2<NR, KJ>(j)], cjs[j]);
             }
             slot ^= 1;
             ++L;
@@ -497,10 +510,10 @@ __global__ void __launch_bounds__(NR* P, MINB)
                 for (int f2 = 0; f2 < NR; ++f2) v[f2] = cf{0.f, 0.f};
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
-                    const int f2 = j < KJ ? j : NR - NJ + j;
+                    const int f2 = band_f2<NR, KJ>(j);
                     const cf term = cmulc(acc[j], cjs[j]);
-                    // wide band: the negative column j lands on a sub-bin that already holds its non-negative alias
-                    v[f2] = (j >= KJ && f2 < KJ) ? cadd(v[f2], term) : term;
+                    // wide band: later columns land on a sub-bin that already holds an alias
+                    v[f2] = band_first<NR, KJ>(j) ? term : cadd(v[f2], term);
                 }
             }
             Dft<NR, +1>::run(v);   // over f2 -> m2

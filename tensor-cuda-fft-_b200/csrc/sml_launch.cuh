@@ -81,8 +81,11 @@ int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map
     SML_CASE(16, 8, 8, 3)
     SML_CASE(16, 12, 8, 3)
     SML_CASE(16, 16, 8, 3)
+    SML_CASE(16, 24, 8, 3)
+    SML_CASE(16, 32, 8, 2)
     SML_CASE(8, 4, 32, 2)
     SML_CASE(8, 8, 32, 2)
+    SML_CASE(8, 16, 32, 2)
 #undef SML_CASE
     return fail("internal: no fast kernel for NR=%d KJ=%d P=%d", p.NR, p.KJ, p.P);
 }

@@ -40,7 +40,9 @@ def test_plan_selection(native):
     assert native.plan(3, 100, 32, 16)["path"] == "generic"      # T is not a multiple of any sub-transform length
     assert native.plan(2, 3072, 768, 384) == {"path": "fast", "M": 1024, "R": 3, "k": 384}    # T = R * M, R = 3
     assert native.plan(2, 1536, 96, 48) == {"path": "fast", "M": 256, "R": 6, "k": 48}
-    assert native.plan(2, 1536, 768, 384)["path"] == "generic"   # needs M = 1024, which does not divide 1536
+    assert native.plan(2, 1536, 768, 384) == {"path": "fast", "M": 256, "R": 6, "k": 384}     # three band bins per sub-bin
+    assert native.plan(2, 1280, 1024, 512) == {"path": "fast", "M": 256, "R": 5, "k": 512}    # four
+    assert native.plan(2, 1536, 1536, 768)["path"] == "generic"  # k = 768 needs M = 1024, which does not divide 1536
     assert native.plan(2, 48, 7, 3)["path"] == "generic"         # odd D
     assert native.plan(2, 16, 64, 32)["k"] == 8                  # k = min(F, T//2)
     assert native.plan(2, 16, 64, 32)["path"] == "generic"       # sub-transform would not fit in T

@@ -96,6 +96,9 @@ SHAPES = [
     (1, 3072, 768, None, "fast"),       # T = 3 * 1024 at the cfg-2 band
     (2, 1536, 96, None, "fast"),        # T = 6 * 256
     (1, 5120, 64, 512, "fast"),         # T = 5 * 1024, k = 512
+    (2, 1536, 768, None, "fast"),       # T = 6 * 256 with k = 384: three band bins per sub-bin (KJ = 24)
+    (1, 1280, 1024, None, "fast"),      # T = 5 * 256 with k = 512: four band bins per sub-bin (KJ = 32)
+    (2, 192, 256, None, "fast"),        # T = 3 * 64 with k = 96 on the 8 x 8 sub-transform (KJ = 16)
     (2, 1000, 40, None, "generic"),     # T not a multiple of 64
     (2, 77, 10, 5, "generic"),          # odd T
     (2, 128, 30, None, "generic"),      # D*4 % 16 != 0
