@@ -440,6 +440,17 @@ def test_cuda_graph_capture(pkg, dev):
         assert torch.equal(a, b.detach())      # same kernels, same inputs: bit-identical (the gradient sum is deterministic)
 
 
+def test_random_stress_vs_torch_fft():
+    # 120 random (B, T, D, F, dtype) problems across every plan family against the reference algorithm (torch.fft + autograd)
+    # on the same GPU -- tools/stress.py exits non-zero on the first mismatch
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "stress.py"), "120", "7"], cwd=root, capture_output=True,
+                         text=True, timeout=900)
+    assert res.returncode == 0 and "stress ok" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+
+
 def test_fresh_process_smoke():
     # a fresh interpreter: the FIRST library call of the autograd worker thread is sml_backward, which must bind the CUDA
     # context itself before the driver-API tensor-map encode (regression: CUDA_ERROR_INVALID_CONTEXT)
