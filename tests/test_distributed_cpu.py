@@ -42,7 +42,8 @@ def _worker(rank, world, port, q, flat_layout=False):
     allreduce_filter_grads([m])
     if flat_layout:     # reduced in place: no concatenation, no copy back
         assert m.weight_real.grad.data_ptr() == ptr and m.bias.grad.data_ptr() == ptr + 24 * 4
-    q.put((rank, mine.shape[0], m.weight_real.grad.clone(), m.weight_imag.grad.clone(), m.bias.grad.clone()))
+    # plain lists: tensors in a multiprocessing queue travel as shared file descriptors, which die with the worker
+    q.put((rank, mine.shape[0], m.weight_real.grad.tolist(), m.weight_imag.grad.tolist(), m.bias.grad.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,6 +69,7 @@ def test_sharded_filter_grad_allreduce(flat_layout):
     want_b = full.sum(dim=(0, 1))
     assert [r[1] for r in res] == [3, 2]
     for _, _, gwr, gwi, gb in res:
+        gwr, gwi, gb = torch.tensor(gwr), torch.tensor(gwi), torch.tensor(gb)
         assert torch.allclose(gb, want_b, atol=1e-5)
         assert torch.allclose(gwr, want_b.unsqueeze(1).repeat(1, 3), atol=1e-5)
         assert torch.allclose(gwi, 2 * want_b.unsqueeze(1).repeat(1, 3), atol=1e-5)
