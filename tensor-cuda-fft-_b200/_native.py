@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libspectral_mix_b200.so")
+LIB_PATH = os.environ.get("SML_LIB_PATH") or os.path.join(_PKG_DIR, "libspectral_mix_b200.so")   # override: A/B of builds
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 DTYPE_F32 = 0

@@ -301,7 +301,7 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         if (launch_fast<IO, true>(p, map, map_out, prm, grid, stream)) return 1;
         if (want_grads) {
             const long long n = (long long)D * ((F + 1) / 2);
-            sml::filtergrad_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(
+            sml::filtergrad_reduce_kernel<<<(unsigned)((n + 63) / 64), dim3(64, 4), 0, stream>>>(
                 reinterpret_cast<const float2*>(prm.gpart), prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k);
             count_launch();
             SML_CUDA(cudaGetLastError());

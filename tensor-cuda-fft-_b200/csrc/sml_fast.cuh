@@ -409,8 +409,11 @@ __global__ void __launch_bounds__(NR* P, MINB)
     // uniform twiddle of pass r for band column j = tid (threads < NJ): W_T^{NR r f2s}, f2s = j (j < KJ) or j - NJ
     auto cj_load = [&](int r) -> float2 {
         const int f2s = tid < KJ ? tid : tid - NJ;
-        int idx = (NR * r * f2s) % T;   // T = R * M need not be a power of two
+        // |NR r f2s| < 2 NR^2 R = 2T (|f2s| <= 2 NR): reduce mod T (not a power of two in general) without a division
+        int idx = NR * r * f2s;
         if (idx < 0) idx += T;
+        if (idx < 0) idx += T;
+        if (idx >= T) idx -= T;
         return __ldg(gtab + idx);
     };
 
@@ -558,27 +561,41 @@ __global__ void __launch_bounds__(NR* P, MINB)
 // batch reduction of the filter / bias gradient terms written by the BWD kernel (wirtinger_ops.py:77-80: sum over dim 0).
 // One thread per (d, pair of bins f, f+1 < F) -- pairs that are not both live or not 16-byte aligned take the scalar tail; also zero-fills the columns f >= k, so no memset is needed.
 // Deterministic (fixed summation order over b).
-static __global__ void filtergrad_reduce_kernel(const float2* __restrict__ gpart, const float* __restrict__ gbpart,
+static __global__ void __launch_bounds__(256) filtergrad_reduce_kernel(const float2* __restrict__ gpart, const float* __restrict__ gbpart,
                                                 float* __restrict__ gw_re, float* __restrict__ gw_im,
                                                 float* __restrict__ gb, int B, int D, int F, int k) {
+    // block (64, 4): threadIdx.x -> pair of bins, threadIdx.y -> every 4th batch element; the four partial sums are combined
+    // through shared memory in a fixed order (b-slices 0, 1, 2, 3), so the result does not depend on scheduling
+    __shared__ float4 part[3][64];
     const int F2 = (F + 1) / 2;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)D * F2) return;
-    const int d = (int)(idx / F2), f = 2 * (int)(idx - (long long)d * F2);
+    const long long idx = (long long)blockIdx.x * 64 + threadIdx.x;
+    const bool valid = idx < (long long)D * F2;
+    const int d = valid ? (int)(idx / F2) : 0, f = valid ? 2 * (int)(idx - (long long)d * F2) : 0;
+    const int by = threadIdx.y;
     float sr0 = 0.f, si0 = 0.f, sr1 = 0.f, si1 = 0.f;
     const size_t stride = (size_t)D * k;
     const float2* p = gpart + (size_t)d * k + f;
-    if (f + 1 < k && ((((size_t)d * k + f) & 1) == 0) && (stride & 1) == 0) {   // both bins live and 16-byte aligned
-#pragma unroll 8
-        for (int b = 0; b < B; ++b) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)b * stride));
-            sr0 += v.x; si0 += v.y; sr1 += v.z; si1 += v.w;
+    if (valid) {
+        if (f + 1 < k && ((((size_t)d * k + f) & 1) == 0) && (stride & 1) == 0) {   // both bins live and 16-byte aligned
+#pragma unroll 4
+            for (int b = by; b < B; b += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)b * stride));
+                sr0 += v.x; si0 += v.y; sr1 += v.z; si1 += v.w;
+            }
+        } else {
+            for (int b = by; b < B; b += 4) {
+                if (f < k) { const float2 v = __ldg(p + (size_t)b * stride); sr0 += v.x; si0 += v.y; }
+                if (f + 1 < k) { const float2 v = __ldg(p + 1 + (size_t)b * stride); sr1 += v.x; si1 += v.y; }
+            }
         }
-    } else {
-        for (int b = 0; b < B; ++b) {
-            if (f < k) { const float2 v = __ldg(p + (size_t)b * stride); sr0 += v.x; si0 += v.y; }
-            if (f + 1 < k) { const float2 v = __ldg(p + 1 + (size_t)b * stride); sr1 += v.x; si1 += v.y; }
-        }
+    }
+    if (by > 0) part[by - 1][threadIdx.x] = make_float4(sr0, si0, sr1, si1);
+    __syncthreads();
+    if (by != 0 || !valid) return;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const float4 q = part[s][threadIdx.x];
+        sr0 += q.x; si0 += q.y; sr1 += q.z; si1 += q.w;
     }
     const size_t o = (size_t)d * F + f;
     gw_re[o] = sr0;

@@ -203,8 +203,11 @@ __global__ void __launch_bounds__(512, 1)
         cf* const cjs = cjbuf + fp2 * NR;         // this warp's private twiddle slot
         auto cj_load = [&](int r) -> float2 {     // lane f2: W_T^{NR r f2s}
             const int f2s = ff1 < NR / 2 ? ff1 : ff1 - NR;
-            int idx = (NR * r * f2s) % T;   // T = R * M need not be a power of two
+            // |NR r f2s| < 2 NR^2 R = 2T (|f2s| <= 2 NR): reduce mod T (not a power of two in general) without a division
+        int idx = NR * r * f2s;
         if (idx < 0) idx += T;
+        if (idx < 0) idx += T;
+        if (idx >= T) idx -= T;
         return __ldg(gtab + idx);
         };
         unsigned int c = 0;
