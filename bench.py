@@ -123,7 +123,8 @@ def run_reference_arm(args):
         return
     B = min(args.cpu_sample_batch, args.batch)
     T, D = args.seq, args.embed
-    dt, n, threads = cpu_reference_step_time(B, T, D, args.steps, max(1, min(args.warmup, 2)))
+    # at most --steps steps, and at most ~90 s of CPU work (the line reports the steps actually timed)
+    dt, n, threads = cpu_reference_step_time(B, T, D, args.steps, max(1, min(args.warmup, 2)), budget_s=90.0)
     val = B * T / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
