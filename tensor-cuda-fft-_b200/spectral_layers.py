@@ -85,6 +85,8 @@ class _SpectralMixFn(torch.autograd.Function):
         io = _IO_DTYPES[x.dtype]
         lib = _native.lib()
         xc = x.contiguous()
+        if xc.data_ptr() % 16:      # a contiguous view at an odd storage offset: the fused kernel's TMA needs 16-byte alignment
+            xc = xc.clone()
         wr, wi = _f32c(w_re), _f32c(w_im)
         bs = None if bias is None else _f32c(bias)
         y = torch.empty_like(xc)
@@ -111,6 +113,8 @@ class _SpectralMixFn(torch.autograd.Function):
         gc = g.contiguous()
         if gc.dtype != (torch.float32 if io == _native.DTYPE_F32 else torch.bfloat16):
             gc = gc.to(torch.float32 if io == _native.DTYPE_F32 else torch.bfloat16)
+        if gc.data_ptr() % 16:
+            gc = gc.clone()
         gx = torch.empty_like(gc)
         want = xlow is not None
         flat = None

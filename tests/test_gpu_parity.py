@@ -385,6 +385,30 @@ def test_language_model_golden(pkg, dev, golden_dir):
     assert text.startswith("ab") and len(text) >= 3
 
 
+def test_unaligned_views(pkg, dev):
+    # contiguous views whose storage offset is not a multiple of 16 bytes (x and the upstream gradient) still work
+    torch.manual_seed(2)
+    B, T, D = 2, 256, 32
+    layer = pkg.SpectralMixingLayer(D).to(dev)
+    with torch.no_grad():
+        layer.weight_real.normal_(); layer.weight_imag.normal_()
+    buf = torch.randn(B * T * D + 3, device=dev)
+    gbuf = torch.randn(B * T * D + 1, device=dev)
+    x = buf[3:].view(B, T, D)
+    g = gbuf[1:].view(B, T, D)
+    assert x.data_ptr() % 16 != 0
+    xr = x.detach().requires_grad_(True)
+    layer(xr).backward(g)
+    xa = x.clone().requires_grad_(True)
+    layer.zero_grad()
+    ya = layer(xa)
+    ya.backward(g.clone())
+    torch.cuda.synchronize()
+    assert torch.equal(xr.grad, xa.grad)
+    with torch.no_grad():
+        assert torch.equal(layer(x), ya.detach())
+
+
 def test_errors_are_loud(pkg, dev):
     # no silent fallback: wrong device, wrong dtype, wrong rank and mismatched filters raise
     layer = pkg.SpectralMixingLayer(32).to(dev)
