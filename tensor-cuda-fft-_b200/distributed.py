@@ -114,10 +114,12 @@ def allreduce_filter_grads(modules: Iterable[torch.nn.Module], group: Optional[d
         flat = torch.cat([g.reshape(-1) for g in grads])
     work = None
     symm = None
-    # measured on 8 x B200 for the 2.4 MB cfg-2 gradient (tools/allreduce_check.py): NCCL 35 us / symmetric-memory multimem
-    # 47 us at 2 ranks, NCCL 64 us / multimem 36 us at 8 ranks -> the switch reduction is the default from 4 ranks up.
-    mode = os.environ.get("SML_ALLREDUCE", "auto")
-    use_symm = mode == "symm" or (mode == "auto" and dist.get_world_size(group) >= 4)
+    # NCCL is the default.  The symmetric-memory path (SML_ALLREDUCE=symm) wins a back-to-back microbenchmark at 8 ranks
+    # (tools/allreduce_check.py: 36 vs 64 us for the 2.4 MB cfg-2 gradient) but loses inside the real step, where the host
+    # runs ahead of the GPU and NCCL's launch cost is hidden: 4 ranks, cfg-2: 0.457 ms per step with NCCL, 0.470 ms with the
+    # copy-in / multimem reduce / copy-out sequence.
+    mode = os.environ.get("SML_ALLREDUCE", "nccl")
+    use_symm = mode == "symm"
     if flat.is_cuda and not async_op and flat.dtype == torch.float32 and use_symm:
         symm = _SymmetricAllReduce.get(flat.numel(), flat.device, group if group is not None else dist.group.WORLD)
     global LAST_ALLREDUCE_PATH
