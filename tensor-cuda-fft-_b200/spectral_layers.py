@@ -209,7 +209,12 @@ class SpectralMixingLayer(nn.Module):
         B, T, D = x.shape
         assert D == self.embed_dim, f"Expected embed_dim={self.embed_dim}, got {D}"
         if self.learnable and self.weight_real is not None:
-            y = _SpectralMixFn.apply(x, self.weight_real, self.weight_imag, self.bias)
+            if x.numel() == 0:      # empty batch or sequence: nothing to transform (the reference returns an empty tensor too)
+                if not x.is_cuda:
+                    raise RuntimeError("SpectralMixingLayer (B200 build) needs a CUDA tensor; there is no CPU path")
+                y = x + 0.0 * (self.weight_real.sum() + self.weight_imag.sum() + self.bias.sum()).to(x.dtype)
+            else:
+                y = _SpectralMixFn.apply(x, self.weight_real, self.weight_imag, self.bias)
         else:
             # learnable=False is fft followed by ifft(.).real (spectral_layers.py:88, :112): the identity up to
             # rounding (reference self-test :301-309 measures 1.2e-7); returned exactly, as a new tensor.

@@ -385,6 +385,16 @@ def test_language_model_golden(pkg, dev, golden_dir):
     assert text.startswith("ab") and len(text) >= 3
 
 
+def test_empty_batch(pkg, dev):
+    # the reference returns an empty tensor for an empty batch (torch.fft on a (0, T, D) tensor); gradients are zeros
+    layer = pkg.SpectralMixingLayer(16).to(dev)
+    x = torch.empty(0, 64, 16, device=dev, requires_grad=True)
+    y = layer(x)
+    assert y.shape == (0, 64, 16)
+    y.sum().backward()
+    assert x.grad.shape == x.shape and layer.weight_real.grad.abs().max().item() == 0.0
+
+
 def test_unaligned_views(pkg, dev):
     # contiguous views whose storage offset is not a multiple of 16 bytes (x and the upstream gradient) still work
     torch.manual_seed(2)
