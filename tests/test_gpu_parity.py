@@ -385,6 +385,48 @@ def test_language_model_golden(pkg, dev, golden_dir):
     assert text.startswith("ab") and len(text) >= 3
 
 
+def test_tensor_larger_than_4gb(pkg, dev):
+    # 5.4 GB per activation tensor (1.34 G elements): byte offsets beyond 32 bits in the TMA maps, X_low and gradient indexing.
+    # Checked through size-independent properties and through slices against the reference algorithm (torch.fft) on the GPU.
+    B, T, D = 40, 32768, 1024
+    Fn = D // 2
+    layer = pkg.SpectralMixingLayer(D).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(11)
+    with torch.no_grad():
+        layer.weight_real.copy_(torch.randn(D, Fn, device=dev, generator=gen))
+        layer.weight_imag.copy_(torch.randn(D, Fn, device=dev, generator=gen))
+        layer.bias.copy_(torch.randn(D, device=dev, generator=gen))
+    x = torch.randn(B, T, D, device=dev, generator=gen)
+    g = torch.randn(B, T, D, device=dev, generator=gen)
+    assert x.numel() * 4 > 2 ** 32
+    xr = x.requires_grad_(True)
+    y = layer(xr)
+    y.backward(g)
+    torch.cuda.synchronize()
+    gx = xr.grad
+
+    def ref_slice(b, d0):
+        xs = x[b:b + 1, :, d0:d0 + 8].detach().double()
+        spec = torch.fft.fft(xs, dim=1)
+        w = torch.complex(layer.weight_real.detach()[d0:d0 + 8].double(), layer.weight_imag.detach()[d0:d0 + 8].double())
+        kept = torch.zeros_like(spec)
+        kept[:, :Fn, :] = spec[:, :Fn, :] * w.T.unsqueeze(0)
+        return torch.fft.ifft(kept, dim=1).real + layer.bias.detach()[d0:d0 + 8].double()
+
+    for (b, d0) in [(0, 0), (B - 1, D - 8), (27, 512)]:      # (27, 512) sits beyond the 4 GB mark
+        want = ref_slice(b, d0)
+        got = y[b:b + 1, :, d0:d0 + 8].detach().double()
+        assert ((got - want).norm() / want.norm()).item() <= TOL_F32
+    # adjoint identity <g, J x> = <J^T g, x> (J = the bias-free linear map) over the whole tensor, accumulated per batch element
+    lhs = rhs = 0.0
+    for b in range(B):
+        lhs += torch.sum(g[b].double() * (y[b].detach().double() - layer.bias.detach().double())).item()
+        rhs += torch.sum(gx[b].double() * x[b].detach().double()).item()
+    assert abs(lhs - rhs) <= 5e-5 * max(abs(lhs), abs(rhs))
+    gb_want = torch.stack([g[b].double().sum(dim=0) for b in range(B)]).sum(dim=0)
+    assert ((layer.bias.grad.double() - gb_want).norm() / gb_want.norm()).item() <= TOL_F32
+
+
 def test_empty_batch(pkg, dev):
     # the reference returns an empty tensor for an empty batch (torch.fft on a (0, T, D) tensor); gradients are zeros
     layer = pkg.SpectralMixingLayer(16).to(dev)
