@@ -124,6 +124,27 @@ def run_lm_case(seed):
     return out
 
 
+def run_hybrid_case(ref_sl, seed):
+    """HybridSpectralAttention (spectral_layers.py:193-256), a caller of the layer: output and input gradient, dropout 0."""
+    torch.manual_seed(seed)
+    D, H, T, B = 32, 4, 64, 2
+    mod = ref_sl.HybridSpectralAttention(D, num_heads=H, dropout=0.0)
+    with torch.no_grad():
+        mod.spectral.weight_real.normal_()
+        mod.spectral.weight_imag.normal_()
+        mod.spectral.bias.normal_()
+    x = torch.randn(B, T, D).requires_grad_(True)
+    g = torch.randn(B, T, D)
+    y = mod(x)
+    y.backward(g)
+    out = {"x": x.detach().numpy(), "g": g.numpy(), "y": y.detach().numpy(), "gx": x.grad.numpy(),
+           "cfg": np.array([D, H, T, B], dtype=np.int64),
+           "grad.spectral.weight_real": mod.spectral.weight_real.grad.numpy(), "grad.qkv.weight": mod.qkv.weight.grad.numpy()}
+    for k, v in mod.state_dict().items():
+        out["sd." + k] = v.numpy()
+    return out
+
+
 def main():
     if not os.path.isdir(REF_ROOT):
         sys.exit(f"{REF_ROOT} not found: golden vectors can only be regenerated where the reference is mounted")
@@ -142,6 +163,7 @@ def main():
     np.savez_compressed(os.path.join(OUT_DIR, "layer_nonlearnable.npz"), x=x.numpy(), y=lay(x).numpy(),
                         n_params=np.int64(sum(p.numel() for p in lay.parameters())))
     np.savez_compressed(os.path.join(OUT_DIR, "wirtinger.npz"), **run_wirtinger_cases(ref_w, seed=4242))
+    np.savez_compressed(os.path.join(OUT_DIR, "hybrid_attention.npz"), **run_hybrid_case(ref_sl, seed=2718))
     np.savez_compressed(os.path.join(OUT_DIR, "lm_small.npz"), **run_lm_case(seed=31337))
     # parameter-count known answer, BENCHMARKS.md:86
     n = sum(p.numel() for p in ref_sl.SpectralMixingLayer(256).parameters())

@@ -361,6 +361,23 @@ def test_full_size_properties(pkg, dev, B, T, D, dtype):
     assert hi <= (1e-9 if dtype == torch.float32 else 1e-3) * lo
 
 
+def test_hybrid_attention_golden(pkg, dev, golden_dir):
+    # HybridSpectralAttention (reference spectral_layers.py:193-256), the other in-file caller of the layer
+    z = np.load(os.path.join(golden_dir, "hybrid_attention.npz"))
+    D, H, T, B = (int(v) for v in z["cfg"])
+    mod = pkg.HybridSpectralAttention(D, num_heads=H, dropout=0.0)
+    mod.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}, strict=True)
+    mod = mod.to(dev)
+    x = torch.from_numpy(z["x"]).to(dev).requires_grad_(True)
+    y = mod(x)
+    y.backward(torch.from_numpy(z["g"]).to(dev))
+    torch.cuda.synchronize()
+    assert orc.rel_l2(y.detach().cpu().numpy(), z["y"]) <= 1e-5
+    assert orc.rel_l2(x.grad.cpu().numpy(), z["gx"]) <= 1e-4
+    assert orc.rel_l2(mod.spectral.weight_real.grad.cpu().numpy(), z["grad.spectral.weight_real"]) <= 1e-4
+    assert orc.rel_l2(mod.qkv.weight.grad.cpu().numpy(), z["grad.qkv.weight"]) <= 1e-4
+
+
 def test_language_model_golden(pkg, dev, golden_dir):
     # SpectralLanguageModel (reference byte_spectral_model.py:105-161) with the fused layer inside: logits, loss and gradients
     # against the unmodified reference run on the CPU (tests/golden/lm_small.npz)
