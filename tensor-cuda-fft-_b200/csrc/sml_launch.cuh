@@ -1,6 +1,7 @@
 // sml_launch.cuh -- template definitions of the fused-kernel launchers (one explicit instantiation per sml_inst_*.cu).
 #pragma once
 
+#include <atomic>
 #include <mutex>
 
 #include "sml_host.h"
@@ -14,6 +15,20 @@ namespace sml_host {
         if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e));    \
     } while (0)
 
+// The opt-in to more than 48 KB of dynamic shared memory is a per-device function attribute: set it once per (kernel
+// instantiation, device) -- a process may drive several GPUs.
+template <typename Kern>
+int ensure_smem_attr(Kern kern, size_t smem_bytes, std::atomic<unsigned long long>& done) {   // done: one bit per device ordinal
+    int dev = 0;
+    SML_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return 0;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return fail("cudaFuncSetAttribute(smem=%zu) failed: %s", smem_bytes, cudaGetErrorString(e));
+    done.fetch_or(bit, std::memory_order_release);
+    return 0;
+}
+
 // two landing tiles fit wherever MINB CTAs per SM still fit into 227 KB of shared memory with them
 template <int NR, int P, int MINB, typename IO>
 constexpr bool xb2_fits() { return (sml::FastCfg<NR, P, IO, 2>::SMEM_BYTES + 1024) * MINB <= 227u * 1024u; }
@@ -23,12 +38,8 @@ int launch_fast_xb(const CUtensorMap& map_in, const CUtensorMap& map_out, const 
                    cudaStream_t stream) {
     using C = sml::FastCfg<NR, P, IO, XB>;
     auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD, XB>;
-    static std::once_flag once;   // one per instantiation
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-    });
-    if (attr_err != cudaSuccess) return fail("cudaFuncSetAttribute(smem=%zu) failed: %s", C::SMEM_BYTES, cudaGetErrorString(attr_err));
+    static std::atomic<unsigned long long> attr_done{0};   // per kernel instantiation (this function template)
+    if (int rc = ensure_smem_attr(kern, C::SMEM_BYTES, attr_done)) return rc;
     kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map_in, map_out, prm);
     count_launch();
     SML_CUDA(cudaGetLastError());
@@ -49,12 +60,8 @@ int launch_ws_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const 
                    cudaStream_t stream) {
     using C = sml::WsCfg<IO>;
     auto kern = sml::sml_ws_kernel<KJ, IO, BWD>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-    });
-    if (attr_err != cudaSuccess) return fail("cudaFuncSetAttribute(smem=%zu) failed: %s", C::SMEM_BYTES, cudaGetErrorString(attr_err));
+    static std::atomic<unsigned long long> attr_done{0};   // per kernel instantiation (this function template)
+    if (int rc = ensure_smem_attr(kern, C::SMEM_BYTES, attr_done)) return rc;
     kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map_in, map_out, prm);
     count_launch();
     SML_CUDA(cudaGetLastError());

@@ -444,6 +444,31 @@ def test_tensor_larger_than_4gb(pkg, dev):
     assert ((layer.bias.grad.double() - gb_want).norm() / gb_want.norm()).item() <= TOL_F32
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(pkg):
+    # per-device state (twiddle tables, shared-memory opt-in of every kernel instantiation, context binding)
+    torch.manual_seed(3)
+    B, T, D = 2, 2048, 96
+    x = torch.randn(B, T, D)
+    g = torch.randn(B, T, D)
+    outs = []
+    for idx in (0, 1, 0):
+        d = torch.device("cuda", idx)
+        layer = pkg.SpectralMixingLayer(D).to(d)
+        with torch.no_grad():
+            layer.weight_real.fill_(0.5)
+            layer.weight_imag.fill_(-0.25)
+        xr = x.to(d).requires_grad_(True)
+        y = layer(xr)
+        y.backward(g.to(d))
+        torch.cuda.synchronize(d)
+        outs.append((y.detach().cpu(), xr.grad.cpu(), layer.weight_real.grad.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs[0], outs[2]):
+        assert torch.equal(a, b)
+
+
 def test_empty_batch(pkg, dev):
     # the reference returns an empty tensor for an empty batch (torch.fft on a (0, T, D) tensor); gradients are zeros
     layer = pkg.SpectralMixingLayer(16).to(dev)
