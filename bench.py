@@ -201,7 +201,8 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no_samples"]}
         reasons = sorted({n for r in inside for n, v in zip(self.NAMES, r[4]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": inside[0][2], "reasons": reasons,
-                "samples": len(inside), "power_w_max": max(r[3] for r in inside), "sampler": "nvidia-smi -lms 10, samples inside the timed region"}
+                "samples": len(inside), "power_w_max": max(r[3] for r in inside),
+                "sampler": "nvidia-smi -lms 10, samples inside the timed region" + ("; " + self.note if getattr(self, "note", None) else "")}
 
 
 def _collective_path():
@@ -286,7 +287,6 @@ def run_ours(args):
     e1.record()
     barrier()
     sampler.mark_end()
-    clocks = sampler.stop()
     launches = _native.launch_count() - n0
     ms_total = e0.elapsed_time(e1)
     if world > 1:
@@ -294,6 +294,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = t.item()
     ms_step = ms_total / args.steps
+    if ms_total < 100.0:
+        # the timed region is shorter than a few sampling periods: keep the same load running (untimed, the same number of
+        # extra steps on every rank) until the sampler has seen ~0.2 s of it, and say so in the clocks record
+        for _ in range(min(5000, int(200.0 / ms_step) + 1)):
+            step()
+        barrier()
+        sampler.t1 = time.time()
+        sampler.note = "timed region < 0.1 s: window extended over an untimed continuation of the same steps"
+    clocks = sampler.stop()
     value = world * B * T / (ms_step * 1e-3)
 
     # ---- per-kernel timing through the raw C ABI (events on the launching stream), for the roofline ----
