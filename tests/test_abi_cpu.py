@@ -14,8 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def native():
     import __graft_entry__ as ge
     from tensor_cuda_fft_b200 import _native
-    if not os.path.exists(_native.LIB_PATH):
-        ge.build()
+    ge.build()      # incremental (make): a no-op when the library is newer than its sources, a rebuild when it is stale or missing
     return _native
 
 
