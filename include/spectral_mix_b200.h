@@ -7,7 +7,9 @@
  * point below cites the reference Python lines it replaces.  All paths are relative to /root/reference.
  *
  * Conventions
- *   - every pointer is a DEVICE pointer on the current CUDA device, owned by the caller, contiguous;
+ *   - every pointer is a DEVICE pointer on the current CUDA device, owned by the caller, contiguous
+ *     (sml_fwd_bwd_host alone takes HOST pointers); activations should be 16-byte aligned: unaligned ones are served
+ *     by the generic kernels, which always need the xlow and workspace buffers;
  *   - activations x/y/g/gx are (B, T, D) row-major, element type given by io_dtype;
  *   - filter parameters and their gradients are fp32 (D, F) row-major, bias (D,)   (spectral_layers.py:57-61);
  *   - k = min(F, T/2) live bins (spectral_layers.py:94); xlow is the library's own layout (B, D, k) complex64;
