@@ -295,6 +295,81 @@ def test_wirtinger_ops_golden(pkg, dev, golden_dir):
     assert orc.rel_l2(filt.weight.imag.grad.cpu().numpy(), z["filt_gw_im"]) <= 1e-6
 
 
+def test_parseval_on_saved_spectrum(pkg, dev):
+    # the reference self-test checks Parseval on torch.fft (spectral_layers.py:277-286); the analogue for the fused analysis:
+    # for a real signal band-limited to |f| < k,  sum_t x^2 = (1/T)(|X_0|^2 + 2 sum_{0<f<k} |X_f|^2)  with X = the X_low the
+    # forward kernel saves -- a size-independent check of the streamed, pruned transform at BASELINE cfg-2's geometry
+    from tensor_cuda_fft_b200 import _native
+    lib = _native.lib()
+    B, T, D = 4, 8192, 768
+    Fn = D // 2
+    k = min(Fn, T // 2)
+    gen = torch.Generator(device=dev).manual_seed(21)
+    spec = torch.zeros(B, T // 2 + 1, D, dtype=torch.complex64, device=dev)
+    spec[:, :k, :] = torch.complex(torch.randn(B, k, D, device=dev, generator=gen), torch.randn(B, k, D, device=dev, generator=gen))
+    spec[:, 0, :] = spec[:, 0, :].real.to(torch.complex64)
+    x = torch.fft.irfft(spec, n=T, dim=1).contiguous()          # exactly band-limited real input
+    wr, wi = torch.randn(D, Fn, device=dev, generator=gen), torch.randn(D, Fn, device=dev, generator=gen)
+    y = torch.empty_like(x)
+    xlow = torch.empty(lib.sml_xlow_bytes(B, T, D, Fn), dtype=torch.uint8, device=dev)
+    _native.check(lib.sml_forward(x.data_ptr(), wr.data_ptr(), wi.data_ptr(), None, y.data_ptr(), xlow.data_ptr(),
+                                  B, T, D, Fn, 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    X = xlow.view(torch.complex64).view(B, D, k)
+    e_time = x.double().pow(2).sum(dim=1)                        # (B, D)
+    mag2 = X.abs().double().pow(2)
+    e_freq = (mag2[:, :, 0] + 2.0 * mag2[:, :, 1:].sum(dim=2)) / T
+    assert ((e_freq - e_time).abs() / e_time).max().item() <= 1e-5
+    # and the saved spectrum is the one the signal was built from (irfft's 1/T is undone by the forward transform)
+    assert ((X.transpose(1, 2) - spec[:, :k, :]).norm() / spec[:, :k, :].norm()).item() <= TOL_F32
+
+
+def test_reference_wirtinger_self_test_mirror(pkg, dev):
+    # the reference's own self-test (wirtinger_ops.py:206-389), step for step, on this package's classes
+    torch.manual_seed(0)
+    # 1. gradients flow to both the real and the imaginary part (:219-249)
+    x = torch.complex(torch.randn(2, 8, 16, device=dev), torch.randn(2, 8, 16, device=dev)).requires_grad_(True)
+    weight_param = pkg.ComplexParameter((16, 4), init_mode="uniform").to(dev)
+    weight = weight_param()
+    y = pkg.WirtingerGradient.apply(x[:, :4, :].contiguous(), weight[:, :4].T.unsqueeze(0).contiguous())
+    torch.abs(y).sum().backward()
+    assert weight_param.real.grad is not None and weight_param.imag.grad is not None
+    assert torch.norm(weight_param.real.grad).item() > 0 and torch.norm(weight_param.imag.grad).item() > 0
+    # and they equal PyTorch's own complex autograd on the same inputs (bit-identical in the reference)
+    xs = x.detach().clone().requires_grad_(True)
+    ws = pkg.ComplexParameter((16, 4), init_mode="uniform").to(dev)
+    ws.load_state_dict(weight_param.state_dict())
+    torch.abs(xs[:, :4, :] * ws()[:, :4].T.unsqueeze(0)).sum().backward()
+    assert orc.rel_l2(weight_param.real.grad.cpu().numpy(), ws.real.grad.cpu().numpy()) <= 1e-6
+    assert orc.rel_l2(weight_param.imag.grad.cpu().numpy(), ws.imag.grad.cpu().numpy()) <= 1e-6
+    # 2. phase can be learned (:251-294): 50 Adam steps towards a unit-modulus target move the phase by > 0.1 rad
+    target_phase = torch.randn(16, 4, device=dev)
+    target = torch.complex(torch.cos(target_phase), torch.sin(target_phase))
+    filt = pkg.WirtingerSpectralFilter(16, 8).to(dev)
+    opt = torch.optim.Adam([{"params": filt.weight.real}, {"params": filt.weight.imag}], lr=0.1)
+    initial_phase = filt.weight.phase()[:, :4].clone()
+    for _ in range(50):
+        opt.zero_grad()
+        loss = torch.mean(torch.abs(filt.weight()[:, :4] - target) ** 2)
+        loss.backward()
+        opt.step()
+    assert torch.norm(filt.weight.phase()[:, :4] - initial_phase).item() > 0.1
+    # 4. magnitude is learned through the filter itself (:337-376), here with the gradient coming through the CUDA kernels
+    filt = pkg.WirtingerSpectralFilter(8, 16).to(dev)
+    initial_mag = filt.weight.magnitude().mean().item()
+    xf = torch.complex(torch.randn(4, 64, 8, device=dev), torch.randn(4, 64, 8, device=dev))
+    tgt = xf.clone()
+    tgt[:, 8:16, :] *= 0.1
+    tgt[:, 16:, :] = 0
+    opt = torch.optim.Adam([{"params": filt.weight.real, "lr": 0.1}, {"params": filt.weight.imag, "lr": 0.1}])
+    for _ in range(20):
+        opt.zero_grad()
+        loss = torch.mean(torch.abs(filt(xf) - tgt) ** 2)
+        loss.backward()
+        opt.step()
+    assert abs(filt.weight.magnitude().mean().item() - initial_mag) > 0.01
+
+
 def test_wirtinger_filter_equals_fused_layer(pkg, dev):
     # fft -> WirtingerSpectralFilter -> ifft.real == SpectralMixingLayer minus bias
     gen = torch.Generator().manual_seed(9)
