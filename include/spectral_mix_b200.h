@@ -78,6 +78,9 @@ int sml_fwd_bwd_host(const void* x, const void* g, const float* w_re, const floa
                      void* gx, float* gw_re, float* gw_im, float* gb, int B, int T, int D, int F, int io_dtype,
                      int chunk_batch);
 
+/* Frees the device staging buffers sml_fwd_bwd_host caches on the current device (they are re-created on the next call). */
+int sml_host_release(void);
+
 /* Wirtinger filter multiply on an already transformed tensor.
  * Replaces WirtingerGradient.forward / .backward, wirtinger_ops.py:34-50 / :53-82.
  * x, g, out, gx: (B, N) complex64 (interleaved re,im); w, gw: (N,) complex64 broadcast over B.

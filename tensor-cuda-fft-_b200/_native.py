@@ -61,6 +61,8 @@ def _declare(lib):
     lib.sml_backward.argtypes = [c_void_p] * 9 + [c_size_t] + [c_int] * 5 + [c_void_p]
     lib.sml_fwd_bwd_host.restype = c_int
     lib.sml_fwd_bwd_host.argtypes = [c_void_p] * 10 + [c_int] * 6
+    lib.sml_host_release.restype = c_int
+    lib.sml_host_release.argtypes = []
     lib.sml_wirtinger_mul_forward.restype = c_int
     lib.sml_wirtinger_mul_forward.argtypes = [c_void_p] * 3 + [c_ll, c_ll, c_void_p]
     lib.sml_wirtinger_mul_backward.restype = c_int
@@ -73,7 +75,7 @@ def _declare(lib):
 
 EXPORTED_SYMBOLS = (
     "sml_abi_version", "sml_last_error", "sml_plan", "sml_xlow_bytes", "sml_workspace_bytes",
-    "sml_forward", "sml_backward", "sml_fwd_bwd_host",
+    "sml_forward", "sml_backward", "sml_fwd_bwd_host", "sml_host_release",
     "sml_wirtinger_mul_forward", "sml_wirtinger_mul_backward",
     "sml_wirtinger_filter_forward", "sml_wirtinger_filter_backward",
     "sml_launch_count", "sml_debug_dump",

@@ -575,6 +575,28 @@ int sml_fwd_bwd_host(const void* x, const void* g, const float* w_re, const floa
     return fwd_bwd_host_impl<__nv_bfloat16>(x, g, w_re, w_im, bias, y, gx, gw_re, gw_im, gb, B, T, D, F, io_dtype, chunk_batch);
 }
 
+int sml_host_release(void) {
+    int dev = 0;
+    SML_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    auto it = g_pipes.find(dev);
+    if (it == g_pipes.end()) return 0;
+    HostPipe& hp = it->second;
+    SML_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < HostPipe::NBUF; ++i) {
+        for (int j = 0; j < 4; ++j) { if (hp.act[i][j]) cudaFree(hp.act[i][j]); hp.act[i][j] = nullptr; }
+        if (hp.xlow[i]) cudaFree(hp.xlow[i]);
+        if (hp.ws[i]) cudaFree(hp.ws[i]);
+        hp.xlow[i] = hp.ws[i] = nullptr;
+    }
+    if (hp.params) cudaFree(hp.params);
+    if (hp.grad_part) cudaFree(hp.grad_part);
+    if (hp.grad_total) cudaFree(hp.grad_total);
+    hp.params = hp.grad_part = hp.grad_total = nullptr;
+    hp.cap_act = hp.cap_xlow = hp.cap_ws = hp.cap_par = 0;
+    return 0;
+}
+
 int sml_wirtinger_mul_forward(const void* x, const void* w, void* out, long long B, long long N, void* stream) {
     if (!x || !w || !out) return fail("null pointer");
     if (B < 1 || N < 1) return fail("invalid shape B=%lld N=%lld", B, N);

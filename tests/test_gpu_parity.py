@@ -260,6 +260,8 @@ def test_host_buffer_pipeline(pkg, dev, B, T, D, dtype, chunk):
         for name, a in zip(NAMES, got):
             assert not a.is_cuda
             assert orc.rel_l2(a.float().numpy(), want[name]) <= tol, (name, rep)
+    from tensor_cuda_fft_b200 import _native
+    assert _native.lib().sml_host_release() == 0     # cached staging buffers are dropped and re-created on demand
     y, gx, gwr, gwi, gb = pkg.spectral_mix_fwd_bwd_host(x, g, w_re, w_im, None, filter_grads=False)
     assert gwr is None and orc.rel_l2(gx.float().numpy(), want["gx"]) <= tol
     assert orc.rel_l2((y.float() + bias).numpy(), want["y"]) <= (tol if dtype == torch.float32 else 2 * tol)
