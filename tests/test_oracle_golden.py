@@ -79,3 +79,23 @@ def test_closed_form_half_weight_identity():
     A[:, :F] = np.fft.fft(x, axis=1)[:, :F] * (wr + 1j * wi).T[None]
     alt = 0.5 * np.fft.irfft(A, n=T, axis=1) + 0.5 * A[:, :1].real / T
     assert orc.rel_l2(alt, out["y"]) < 1e-13
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_two_restatements_agree_on_random_shapes(seed):
+    # the torch port (same torch.fft calls as the reference) and the float64 closed form share no code: they must agree
+    # on arbitrary shapes, including T = 1 (k = 0), T = 2 (DC only), odd T and num_filters > T // 2
+    rng = np.random.default_rng(seed)
+    B = int(rng.integers(1, 4))
+    T = int(rng.choice([1, 2, 3, 5, 16, 31, 64, 100, 257]))
+    D = int(rng.integers(1, 9))
+    F = int(rng.integers(1, 2 * D + 3))
+    gen = torch.Generator().manual_seed(seed)
+    x, g = torch.randn(B, T, D, generator=gen), torch.randn(B, T, D, generator=gen)
+    w_re, w_im, bias = torch.randn(D, F, generator=gen), torch.randn(D, F, generator=gen), torch.randn(D, generator=gen)
+    port = orc.torch_port_fwd_bwd(x, w_re, w_im, bias, g)
+    ref = orc.closed_form_f64(x.numpy(), w_re.numpy(), w_im.numpy(), bias.numpy(), g.numpy())
+    for (name, _), got in zip(KEYS, port):
+        want = ref[name]
+        scale = max(np.linalg.norm(want), 1e-6 * max(np.linalg.norm(ref["gw_re"]), 1.0))
+        assert np.linalg.norm(got.numpy().astype(np.float64) - want) / scale <= 2e-5, (name, B, T, D, F)
