@@ -124,6 +124,32 @@ def run_lm_case(seed):
     return out
 
 
+def run_byte_encoder_edge_cases(seed):
+    """ByteSpectralEmbedding (byte_spectral_model.py:20-102) on inputs whose spectrum has EXACTLY zero bins -- a constant
+    byte, period-2 / period-4 sequences, a zero-padded prompt: the reference's per-position loop sees angle(0) = 0 there
+    at every position, which a shift-theorem restatement has to reproduce."""
+    import types
+    ref_sl = load_reference("spectral_layers")
+    pkg = types.ModuleType("fft_tensor")
+    pkg.__path__ = []
+    sys.modules["fft_tensor"], sys.modules["fft_tensor.spectral_layers"] = pkg, ref_sl
+    ref_bm = load_reference("byte_spectral_model")
+    torch.manual_seed(seed)
+    E, T = 32, 64
+    enc = ref_bm.ByteSpectralEmbedding(E, T)
+    with torch.no_grad():
+        enc.freq_bands.uniform_(0.5, 1.5)
+    rows = [[65] * T, [97, 98] * (T // 2), [1, 2, 3, 4] * (T // 4), [0] * T,
+            [ord(c) for c in "the quick brown fox"] + [0] * (T - 19), [200] * (T - 1) + [7]]
+    ids = torch.tensor(rows, dtype=torch.long)
+    with torch.no_grad():
+        emb = enc(ids)
+    out = {"ids": ids.numpy(), "emb": emb.numpy(), "cfg": np.array([E, T], dtype=np.int64)}
+    for k, v in enc.state_dict().items():
+        out["sd." + k] = v.numpy()
+    return out
+
+
 def run_hybrid_case(ref_sl, seed):
     """HybridSpectralAttention (spectral_layers.py:193-256), a caller of the layer: output and input gradient, dropout 0."""
     torch.manual_seed(seed)
@@ -150,6 +176,10 @@ def main():
         sys.exit(f"{REF_ROOT} not found: golden vectors can only be regenerated where the reference is mounted")
     torch.set_num_threads(1)
     os.makedirs(OUT_DIR, exist_ok=True)
+    if "--only-byte-edge" in sys.argv:     # added in round 2: leaves the round-1 fixtures untouched
+        np.savez_compressed(os.path.join(OUT_DIR, "byte_encoder_edge.npz"), **run_byte_encoder_edge_cases(seed=909))
+        print("wrote byte_encoder_edge.npz")
+        return
     ref_sl = load_reference("spectral_layers")
     ref_w = load_reference("wirtinger_ops")
     for i, case in enumerate(LAYER_CASES):
@@ -165,6 +195,7 @@ def main():
     np.savez_compressed(os.path.join(OUT_DIR, "wirtinger.npz"), **run_wirtinger_cases(ref_w, seed=4242))
     np.savez_compressed(os.path.join(OUT_DIR, "hybrid_attention.npz"), **run_hybrid_case(ref_sl, seed=2718))
     np.savez_compressed(os.path.join(OUT_DIR, "lm_small.npz"), **run_lm_case(seed=31337))
+    np.savez_compressed(os.path.join(OUT_DIR, "byte_encoder_edge.npz"), **run_byte_encoder_edge_cases(seed=909))
     # parameter-count known answer, BENCHMARKS.md:86
     n = sum(p.numel() for p in ref_sl.SpectralMixingLayer(256).parameters())
     assert n == 65792, n

@@ -6,7 +6,10 @@ Same classes, constructor signatures and ``state_dict`` keys.  One deliberate di
 ``ByteSpectralEmbedding.forward`` loops over positions in Python and runs one roll + FFT per position (:63-94, the
 documented 50-of-56 ms bottleneck).  By the shift theorem ``fft(roll(s, -p))[f] = fft(s)[f] * exp(+2 pi i f p / T)``, so the
 magnitude is position independent and the phase advances linearly: the loop collapses to ONE FFT plus elementwise work.
-The result is the same up to fp32 rounding (the reference's angle() wraps, sin/cos of it do not care).
+The result is the same up to fp32 rounding (the reference's angle() wraps, sin/cos of it do not care).  Bins that are
+EXACTLY zero (a constant byte, periodic or zero-padded sequences) are the one place where the shift theorem says nothing:
+the reference sees angle(0) = 0 at every position there, so the phase ramp is masked on those bins
+(tests/golden/byte_encoder_edge.npz pins it against the unmodified reference).
 """
 from __future__ import annotations
 
@@ -44,7 +47,8 @@ class ByteSpectralEmbedding(nn.Module):
         pos = torch.arange(T, device=byte_ids.device, dtype=torch.float32)
         f = torch.arange(k, device=byte_ids.device, dtype=torch.float32)
         ramp = (2.0 * math.pi / T) * torch.outer(pos, f)                  # (T, k): phase advance of bin f at position pos
-        phase = torch.angle(spec).unsqueeze(1) + ramp.unsqueeze(0)        # (B, T, k)   == angle(fft(roll(s, -pos)))  :72
+        live = (spec != 0).unsqueeze(1)                                   # an exactly-zero bin stays zero under every roll: angle 0
+        phase = torch.angle(spec).unsqueeze(1) + ramp.unsqueeze(0) * live  # (B, T, k)  == angle(fft(roll(s, -pos)))  :72
         feats = torch.cat([mag.unsqueeze(1).expand(B, T, k), torch.sin(phase), torch.cos(phase)], dim=-1)   # :80-84
         if feats.size(-1) < E:                                            # :87-91
             feats = F.pad(feats, (0, E - feats.size(-1)))
