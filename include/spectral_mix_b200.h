@@ -13,8 +13,9 @@
  *   - activations x/y/g/gx are (B, T, D) row-major, element type given by io_dtype;
  *   - filter parameters and their gradients are fp32 (D, F) row-major, bias (D,)   (spectral_layers.py:57-61);
  *   - k = min(F, T/2) live bins (spectral_layers.py:94); xlow is the library's own layout (B, D, k) complex64;
- *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it, no internal sync
- *     (the first call for a new (device, T) builds a twiddle table and synchronises that stream once);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it, no internal sync.  Exception: the first
+ *     call for a new (device, T) allocates and fills constant tables and synchronises once -- warm a shape up before
+ *     capturing it in a CUDA graph (a first call on a capturing stream fails with a message saying so);
  *   - return value 0 = ok; non-zero = error, message from sml_last_error() (thread local);
  *     an unsupported argument is an error, never a silent fallback.
  */
@@ -80,6 +81,12 @@ int sml_fwd_bwd_host(const void* x, const void* g, const float* w_re, const floa
 
 /* Frees the device staging buffers sml_fwd_bwd_host caches on the current device (they are re-created on the next call). */
 int sml_host_release(void);
+
+/* Frees the constant tables the library keeps per (device, T) -- twiddles, DFT matrices of the tensor-core path -- on every
+ * device (synchronises the current device first; the next call for a shape rebuilds its tables).  Long-running hosts that
+ * sweep many sequence lengths (the reference's generate() grows T by one per step, byte_spectral_model.py:163-208) call
+ * this to bound the cache. */
+int sml_release(void);
 
 /* Wirtinger filter multiply on an already transformed tensor.
  * Replaces WirtingerGradient.forward / .backward, wirtinger_ops.py:34-50 / :53-82.

@@ -63,6 +63,8 @@ def _declare(lib):
     lib.sml_fwd_bwd_host.argtypes = [c_void_p] * 10 + [c_int] * 6
     lib.sml_host_release.restype = c_int
     lib.sml_host_release.argtypes = []
+    lib.sml_release.restype = c_int
+    lib.sml_release.argtypes = []
     lib.sml_wirtinger_mul_forward.restype = c_int
     lib.sml_wirtinger_mul_forward.argtypes = [c_void_p] * 3 + [c_ll, c_ll, c_void_p]
     lib.sml_wirtinger_mul_backward.restype = c_int
@@ -78,7 +80,7 @@ EXPORTED_SYMBOLS = (
     "sml_forward", "sml_backward", "sml_fwd_bwd_host", "sml_host_release",
     "sml_wirtinger_mul_forward", "sml_wirtinger_mul_backward",
     "sml_wirtinger_filter_forward", "sml_wirtinger_filter_backward",
-    "sml_launch_count", "sml_debug_dump",
+    "sml_launch_count", "sml_debug_dump", "sml_release",
 )
 
 

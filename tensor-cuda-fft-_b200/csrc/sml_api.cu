@@ -35,11 +35,40 @@ int fail(const char* fmt, ...) {
     return 1;
 }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+const Knobs& knobs() {
+    static const Knobs k = [] {
+        Knobs v;
+        if (const char* e = getenv("SML_FAST_CTAS")) v.fast_ctas = atoi(e);
+        if (const char* e = getenv("SML_FAST_XB")) v.fast_xb = atoi(e);
+        if (const char* e = getenv("SML_TC")) v.tc = atoi(e) != 0 ? 1 : 0;
+        return v;
+    }();
+    return k;
+}
+
+int get_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (err == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    if (fn == nullptr) return fail("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(err));
+    *out = fn;
+    return 0;
+}
 }   // namespace sml_host
 
 namespace {
 using sml_host::count_launch;
 using sml_host::fail;
+using sml_host::EncodeTiledFn;
+using sml_host::get_encode_fn;
+using sml_host::knobs;
 using sml_host::launch_fast;
 using sml_host::Plan;
 
@@ -102,6 +131,9 @@ int twiddle_table(DeviceState* st, int T, cudaStream_t stream, const sml::cf** o
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = st->twiddles.find(T);
     if (it == st->twiddles.end()) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+            return fail("first call for T=%d on this device builds a twiddle table: run the shape once before capturing a CUDA graph", T);
         sml::cf* tab = nullptr;
         SML_CUDA(cudaMalloc(&tab, sizeof(sml::cf) * (size_t)T));
         sml::twiddle_table_kernel<<<(T + 255) / 256, 256, 0, stream>>>(tab, T);
@@ -148,48 +180,21 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
             else p.KJ = need <= 4 ? 4 : need <= 8 ? 8 : 16;
             if (p.NR == 16 && p.KJ == 32) p.ctas_per_sm = 2;   // 128 accumulator registers
             if (p.NR == 32 && p.KJ >= 16) p.ctas_per_sm = 2;   // 64+ accumulator registers: 3 CTAs/SM would spill
-            if (const char* e = getenv("SML_FAST_CTAS")) {   // tuning knob for the NR=32, KJ=12 kernel: 2 or 3 CTAs per SM
-                if (atoi(e) == 2 && p.NR == 32 && p.KJ == 12) p.ctas_per_sm = 2;
-            }
+            if (knobs().fast_ctas == 2 && p.NR == 32 && p.KJ == 12) p.ctas_per_sm = 2;   // tuning knob: 2 or 3 CTAs per SM
             // (P = 6, i.e. 48-byte rows and 2 CTAs of 6 warps per SM, was measured at 0.320 ms per forward launch against
             //  0.197 ms for P = 4: rows that are not a multiple of the 32-byte sector straddle sectors on loads and stores.)
             // TMA landing tiles: two (loads run two passes ahead) pay off for the small sub-transforms (measured at
             // (32, 8192, 256) fp32: 0.152 vs 0.167 ms per forward launch); at M = 1024 one tile is faster (bf16 cfg-2: 0.203 vs
             // 0.208 ms, cfg-3 fp32: 0.592 vs 0.597 ms) and for fp32 two do not fit next to three CTAs per SM anyway.
             p.xb = p.NR <= 16 ? 2 : 1;
-            if (const char* e = getenv("SML_FAST_XB")) p.xb = atoi(e) == 2 ? 2 : 1;   // tuning knob
-            if (p.NR == 32) {   // M = 1024: warp-specialised kernel, 8 pairs (64-byte TMA rows) per CTA, one CTA per SM
-                p.ws = false;   // experimental (opt-in) until it is parity-green on the GPU
-                if (const char* e = getenv("SML_FAST_WS")) p.ws = atoi(e) != 0;   // tuning knob: 1 = warp-specialised kernel
-                if (p.KJ > 16) p.ws = false;   // the wide band (k > 512) only exists in the lockstep kernel
-                if (p.ws) { p.P = 8; p.ctas_per_sm = 1; }
-            }
+            if (knobs().fast_xb) p.xb = knobs().fast_xb == 2 ? 2 : 1;   // tuning knob
+            // bf16 I/O is compute-bound on the CUDA-core butterflies: eligible problems run the four DFT stages on the
+            // tensor cores instead (sml_tc.cuh).  SML_TC=0 keeps the CUDA-core kernel.
+            p.tc = sml_host::tc_eligible(T, D, p.k, io_dtype) && knobs().tc > 0;
             return p;
         }
     }
     return p;
-}
-
-// ------------------------------------------------------------------------------------------------
-// TMA descriptor (driver entry point resolved through the runtime: no link-time libcuda dependency)
-// ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int get_encode_fn(EncodeTiledFn* out) {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
-        if (err == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
-    });
-    if (fn == nullptr) return fail("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(err));
-    *out = fn;
-    return 0;
 }
 
 // view of a (B, T, D) activation as the 4-D tensor {D, R, M, B}: t = R*m + r
@@ -228,6 +233,14 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
     if (twiddle_table(st, T, stream, &gtab)) return 1;
     const float invT = 1.0f / (float)T;
     const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+    if (p.path == SML_PATH_FAST && aligned && p.tc) {
+        sml_host::TcLaunch a;
+        a.w_re = w_re; a.w_im = w_im; a.bias = bias;
+        a.xlow = reinterpret_cast<sml::cf*>(xlow);
+        a.B = B; a.T = T; a.D = D; a.F = F; a.k = p.k;
+        a.dbg = debug_record();
+        return sml_host::launch_tc<false>(x, y, a, st->sm_count, stream);
+    }
     if (p.path == SML_PATH_FAST && aligned) {
         CUtensorMap map, map_out;
         if (encode_act_map(&map, x, B, T, D, io_dtype, p)) return 1;
@@ -281,6 +294,25 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         const size_t need_ws = part_bytes + sizeof(float) * (size_t)B * D;
         if (want_grads && (ws == nullptr || ws_bytes < need_ws))
             return fail("workspace too small: need %zu bytes (sml_workspace_bytes), got %zu", need_ws, ws_bytes);
+        sml::cf* const gpart = want_grads ? reinterpret_cast<sml::cf*>(ws) : nullptr;
+        float* const gbpart = want_grads ? reinterpret_cast<float*>(static_cast<char*>(ws) + part_bytes) : nullptr;
+        if (p.tc) {
+            sml_host::TcLaunch a;
+            a.w_re = w_re; a.w_im = w_im;
+            a.xlow = reinterpret_cast<sml::cf*>(const_cast<void*>(xlow));
+            a.gw_re = gw_re; a.gpart = gpart; a.gbpart = gbpart;
+            a.B = B; a.T = T; a.D = D; a.F = F; a.k = p.k;
+            a.dbg = debug_record();
+            if (sml_host::launch_tc<true>(g, gx, a, st->sm_count, stream)) return 1;
+            if (want_grads) {
+                const long long n = (long long)D * ((F + 1) / 2);
+                sml::filtergrad_reduce_kernel<<<(unsigned)((n + 63) / 64), dim3(64, 4), 0, stream>>>(
+                    reinterpret_cast<const float2*>(gpart), gbpart, gw_re, gw_im, gb, B, D, F, p.k);
+                count_launch();
+                SML_CUDA(cudaGetLastError());
+            }
+            return 0;
+        }
         CUtensorMap map, map_out;
         if (encode_act_map(&map, g, B, T, D, io_dtype, p)) return 1;
         if (encode_act_map(&map_out, gx, B, T, D, io_dtype, p)) return 1;
@@ -359,7 +391,31 @@ struct HostPipe {
 std::mutex g_pipe_mu;
 std::map<int, HostPipe> g_pipes;
 
+void pipe_free(HostPipe& hp) {   // drops every device buffer and resets the capacities (streams and events stay)
+    for (int i = 0; i < HostPipe::NBUF; ++i) {
+        for (int j = 0; j < 4; ++j) { if (hp.act[i][j]) cudaFree(hp.act[i][j]); hp.act[i][j] = nullptr; }
+        if (hp.xlow[i]) cudaFree(hp.xlow[i]);
+        if (hp.ws[i]) cudaFree(hp.ws[i]);
+        hp.xlow[i] = hp.ws[i] = nullptr;
+    }
+    if (hp.params) cudaFree(hp.params);
+    if (hp.grad_part) cudaFree(hp.grad_part);
+    if (hp.grad_total) cudaFree(hp.grad_total);
+    hp.params = hp.grad_part = hp.grad_total = nullptr;
+    hp.cap_act = hp.cap_xlow = hp.cap_ws = hp.cap_par = 0;
+}
+
+int pipe_reserve_impl(HostPipe& hp, size_t act_bytes, size_t xlow_bytes, size_t ws_bytes, size_t par_floats);
 int pipe_reserve(HostPipe& hp, size_t act_bytes, size_t xlow_bytes, size_t ws_bytes, size_t par_floats) {
+    const int rc = pipe_reserve_impl(hp, act_bytes, xlow_bytes, ws_bytes, par_floats);
+    if (rc != 0) {   // a cudaMalloc failed half way: never leave NULL slots behind a capacity that says they exist
+        cudaDeviceSynchronize();
+        pipe_free(hp);
+    }
+    return rc;
+}
+
+int pipe_reserve_impl(HostPipe& hp, size_t act_bytes, size_t xlow_bytes, size_t ws_bytes, size_t par_floats) {
     if (!hp.ready) {
         SML_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
         SML_CUDA(cudaStreamCreateWithFlags(&hp.s_cmp, cudaStreamNonBlocking));
@@ -412,6 +468,11 @@ int pipe_reserve(HostPipe& hp, size_t act_bytes, size_t xlow_bytes, size_t ws_by
 }
 
 template <typename IO>
+int fwd_bwd_host_body(HostPipe& hp, const void* x, const void* g, const float* w_re, const float* w_im, const float* bias, void* y,
+                      void* gx, float* gw_re, float* gw_im, float* gb, int B, int T, int D, int F, int io_dtype,
+                      int chunk_batch);
+
+template <typename IO>
 int fwd_bwd_host_impl(const void* x, const void* g, const float* w_re, const float* w_im, const float* bias, void* y,
                       void* gx, float* gw_re, float* gw_im, float* gb, int B, int T, int D, int F, int io_dtype,
                       int chunk_batch) {
@@ -419,6 +480,21 @@ int fwd_bwd_host_impl(const void* x, const void* g, const float* w_re, const flo
     SML_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_pipe_mu);   // one host-pipeline call per device at a time
     HostPipe& hp = g_pipes[dev];
+    const int rc = fwd_bwd_host_body<IO>(hp, x, g, w_re, w_im, bias, y, gx, gw_re, gw_im, gb, B, T, D, F, io_dtype, chunk_batch);
+    if (rc != 0 && hp.ready) {
+        // an error in the middle of the pipeline: asynchronous copies into the caller's host buffers may still be in
+        // flight -- drain all three streams before reporting the failure (the caller may free y / gx right away)
+        cudaStreamSynchronize(hp.s_in);
+        cudaStreamSynchronize(hp.s_cmp);
+        cudaStreamSynchronize(hp.s_out);
+    }
+    return rc;
+}
+
+template <typename IO>
+int fwd_bwd_host_body(HostPipe& hp, const void* x, const void* g, const float* w_re, const float* w_im, const float* bias, void* y,
+                      void* gx, float* gw_re, float* gw_im, float* gb, int B, int T, int D, int F, int io_dtype,
+                      int chunk_batch) {
     const size_t esz = sizeof(IO);
     const size_t row_bytes = (size_t)T * D * esz;                 // one batch element
     int cb = chunk_batch;
@@ -431,6 +507,7 @@ int fwd_bwd_host_impl(const void* x, const void* g, const float* w_re, const flo
     if (cb > B) cb = B;
     const size_t nW = (size_t)D * F, nP = 2 * nW + D;
     const bool want_grads = gw_re != nullptr;
+    const bool fast_plan = make_plan(T, D, F, io_dtype).path == SML_PATH_FAST;
     if (want_grads && (gw_im == nullptr || gb == nullptr)) return fail("gw_re, gw_im and gb must be given together");
     if (pipe_reserve(hp, (size_t)cb * row_bytes, sml_xlow_bytes(cb, T, D, F), sml_workspace_bytes(cb, T, D, F, io_dtype), nP))
         return 1;
@@ -456,7 +533,7 @@ int fwd_bwd_host_impl(const void* x, const void* g, const float* w_re, const flo
         // forward: wait for x and for the slot's y/gx to have left (D2H of chunk i - NBUF)
         SML_CUDA(cudaStreamWaitEvent(hp.s_cmp, hp.ev_x[s], 0));
         if (i >= HostPipe::NBUF) SML_CUDA(cudaStreamWaitEvent(hp.s_cmp, hp.ev_out[s], 0));
-        if (forward_impl<IO>(dx, d_wre, d_wim, d_bias, dy, want_grads || hp.cap_ws ? hp.xlow[s] : nullptr, nb, T, D, F,
+        if (forward_impl<IO>(dx, d_wre, d_wim, d_bias, dy, want_grads || !fast_plan ? hp.xlow[s] : nullptr, nb, T, D, F,
                              io_dtype, hp.s_cmp))
             return 1;
         SML_CUDA(cudaEventRecord(hp.ev_fwd[s], hp.s_cmp));
@@ -495,7 +572,7 @@ int fwd_bwd_host_impl(const void* x, const void* g, const float* w_re, const flo
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int sml_abi_version(void) { return 1; }
+int sml_abi_version(void) { return 2; }
 
 const char* sml_last_error(void) { return g_err; }
 
@@ -583,18 +660,21 @@ int sml_host_release(void) {
     if (it == g_pipes.end()) return 0;
     HostPipe& hp = it->second;
     SML_CUDA(cudaDeviceSynchronize());
-    for (int i = 0; i < HostPipe::NBUF; ++i) {
-        for (int j = 0; j < 4; ++j) { if (hp.act[i][j]) cudaFree(hp.act[i][j]); hp.act[i][j] = nullptr; }
-        if (hp.xlow[i]) cudaFree(hp.xlow[i]);
-        if (hp.ws[i]) cudaFree(hp.ws[i]);
-        hp.xlow[i] = hp.ws[i] = nullptr;
-    }
-    if (hp.params) cudaFree(hp.params);
-    if (hp.grad_part) cudaFree(hp.grad_part);
-    if (hp.grad_total) cudaFree(hp.grad_total);
-    hp.params = hp.grad_part = hp.grad_total = nullptr;
-    hp.cap_act = hp.cap_xlow = hp.cap_ws = hp.cap_par = 0;
+    pipe_free(hp);
     return 0;
+}
+
+int sml_release(void) {
+    // constant tables (twiddles, DFT matrices) of every device this process has used; they are rebuilt on the next call
+    SML_CUDA(cudaDeviceSynchronize());
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (auto& dv : g_dev) {
+            for (auto& kv : dv.second.twiddles) cudaFree(kv.second);
+            dv.second.twiddles.clear();
+        }
+    }
+    return sml_host::tc_release_tables();
 }
 
 int sml_wirtinger_mul_forward(const void* x, const void* w, void* out, long long B, long long N, void* stream) {

@@ -101,9 +101,17 @@ static __device__ __noinline__ void mbar_timeout(unsigned int* dbg, uint32_t tag
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg = nullptr, uint32_t tag = 0,
                                           uint32_t aux = 0) {
-    // bounded spin: a lost TMA completion becomes a trap (reported as a launch failure) instead of a hung GPU
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 24)) mbar_timeout(dbg, tag, parity, aux);
+    // bounded wait: a lost completion becomes a trap (reported as a launch failure) instead of a hung GPU.  The bound is
+    // wall-clock time (10 s on %globaltimer, sampled every 2^16 polls), not a poll count, so a healthy kernel that is
+    // time-sliced (MPS, preemption, a debugger) is not killed by it.
+    uint64_t t0 = 0;
+    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
+        if ((spins & 0xFFFFu) == 0u) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ull) mbar_timeout(dbg, tag, parity, aux);
+        }
     }
 }
 // 4-D tiled TMA load global -> shared, completion signalled on an mbarrier (SASS: UTMALDG)

@@ -16,8 +16,39 @@ struct Plan {
     int NR = 0, KJ = 0, P = 0, M = 0, R = 0;
     int ctas_per_sm = 1;
     int xb = 1;        // TMA landing tiles (2 only where the kernel variant was built with them)
-    bool ws = false;   // warp-specialised 512-thread kernel (NR = 32 only)
+    bool tc = false;   // tensor-core (tcgen05) kernel of sml_tc.cuh: bf16 I/O, D % 32 == 0, T % 512 == 0, k <= 512
 };
+
+// tuning knobs from the environment, read once per process (SML_FAST_CTAS, SML_FAST_XB, SML_TC)
+struct Knobs {
+    int fast_ctas = 0;   // 2 or 3: CTAs per SM of the NR = 32, KJ = 12 kernel (0 = default)
+    int fast_xb = 0;     // 1 or 2: TMA landing tiles (0 = default)
+    int tc = -1;         // 0 / 1: tensor-core kernel for eligible bf16 problems (-1 = default)
+};
+const Knobs& knobs();
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency)
+int get_encode_fn(EncodeTiledFn* out);
+
+// ---- tensor-core path (sml_inst_tc.cu) ----
+struct TcLaunch {
+    const float* w_re = nullptr;
+    const float* w_im = nullptr;
+    const float* bias = nullptr;
+    sml::cf* xlow = nullptr;
+    float* gw_re = nullptr;
+    sml::cf* gpart = nullptr;
+    float* gbpart = nullptr;
+    int B = 0, T = 0, D = 0, F = 0, k = 0;
+    unsigned int* dbg = nullptr;
+};
+bool tc_eligible(int T, int D, int k, int io_dtype);
+template <bool BWD>
+int launch_tc(const void* in, void* out, const TcLaunch& a, int sm_count, cudaStream_t stream);
+int tc_release_tables();
 
 // records the message returned by sml_last_error() and returns 1
 int fail(const char* fmt, ...);

@@ -5,7 +5,6 @@
 #include <mutex>
 
 #include "sml_host.h"
-#include "sml_fast_ws.cuh"
 
 namespace sml_host {
 
@@ -55,27 +54,9 @@ int launch_fast_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, cons
     return launch_fast_xb<NR, KJ, P, MINB, IO, BWD, 1>(map_in, map_out, prm, grid, stream);
 }
 
-template <int KJ, typename IO, bool BWD>
-int launch_ws_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
-                   cudaStream_t stream) {
-    using C = sml::WsCfg<IO>;
-    auto kern = sml::sml_ws_kernel<KJ, IO, BWD>;
-    static std::atomic<unsigned long long> attr_done{0};   // per kernel instantiation (this function template)
-    if (int rc = ensure_smem_attr(kern, C::SMEM_BYTES, attr_done)) return rc;
-    kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map_in, map_out, prm);
-    count_launch();
-    SML_CUDA(cudaGetLastError());
-    return 0;
-}
-
 template <typename IO, bool BWD>
 int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm,
                 int grid, cudaStream_t stream) {
-    if (p.ws) {
-        if (p.KJ == 8) return launch_ws_inst<8, IO, BWD>(map_in, map_out, prm, grid, stream);
-        if (p.KJ == 12) return launch_ws_inst<12, IO, BWD>(map_in, map_out, prm, grid, stream);
-        return launch_ws_inst<16, IO, BWD>(map_in, map_out, prm, grid, stream);
-    }
 #define SML_CASE(NR_, KJ_, P_, MINB_) \
     if (p.NR == NR_ && p.KJ == KJ_ && p.P == P_ && p.ctas_per_sm == MINB_) return launch_fast_inst<NR_, KJ_, P_, MINB_, IO, BWD>(map_in, map_out, prm, grid, stream, p.xb);
     SML_CASE(32, 8, 4, 3)

@@ -106,6 +106,7 @@ class _SpectralMixFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable      # double backward is not implemented (the reference never uses it): fail clearly
     def backward(ctx, g):
         wr, wi, xlow = ctx.saved_tensors
         B, T, D, Fn, io = ctx.shape

@@ -174,22 +174,27 @@ static void put_bf(std::vector<unsigned char>& img, uint32_t off, float v) {
 typedef CUresult (*EncFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                           const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-__global__ void tma_dump_kernel(const __grid_constant__ CUtensorMap tm, unsigned char* out, int n0) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t bar;
+__global__ void tma_dump_kernel(const __grid_constant__ CUtensorMap tm, unsigned char* out, int c0, int c1, int c2, int bytes) {
+    extern __shared__ __align__(1024) unsigned char smem[];   // 32 KB data area (pre-filled with 0xFF) + barrier; no static shared memory
+    uint64_t& bar = *reinterpret_cast<uint64_t*>(smem + 32768);
+    for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0xFFFFFFFFu;
+    if (threadIdx.x == 0 && (s32(smem) & 1023u)) printf("T5: dynamic shared base 0x%x is not 1024-byte aligned\n", s32(smem));
+    __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&bar)), "r"(8192) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&bar)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(s32(smem)), "l"((uint64_t)&tm), "r"(s32(&bar)), "r"(32), "r"(n0), "r"(0) : "memory");
+                     ::"r"(s32(smem)), "l"((uint64_t)&tm), "r"(s32(&bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
     }
     __syncthreads();
     uint32_t ok = 0;
     for (uint32_t spin = 0; !ok && spin < (1u << 22); ++spin)
         asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\nselp.u32 %0,1,0,q;\n}\n" : "=r"(ok) : "r"(s32(&bar)) : "memory");
-    if (!ok) __trap();
-    for (int i = threadIdx.x; i < 8192; i += blockDim.x) out[i] = smem[i];
+    if (!ok) { if (threadIdx.x == 0) printf("T5: TMA completion timed out\n"); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32768; i += blockDim.x) out[i] = smem[i];
 }
 
 int main(int argc, char** argv) {
@@ -278,13 +283,37 @@ int main(int argc, char** argv) {
         }
         return run_mma_test("T4 A=K/SW128 rows, B=MN/SW128 view of a [64][128B] table", M, N, K, A, B, aimg, bimg, p, 2e-3);
     }
+    if (test == 7) {
+        // D[128 x 64] = A[128 x 64] * B[64 x 64]^T ; A MN-major SWIZZLE_64B: four MN groups of 32 rows (one per n), each [64 k][64 B]
+        const int M = 128, N = 64, K = 64;
+        std::vector<float> A(M * K), B(N * K);
+        fill(A, 11, true); fill(B, 12, true);
+        std::vector<unsigned char> aimg(4 * 4096, 0), bimg(64 * 128, 0);
+        for (int m = 0; m < M; ++m)
+            for (int k = 0; k < K; ++k) {
+                const uint32_t g = m / 32, mm = m % 32;
+                const uint32_t lin = k * 64 + mm * 2;
+                put_bf(aimg, g * 4096 + (lin ^ (((lin >> 7) & 3u) << 4)), A[m * K + k]);
+            }
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < K; ++k) put_bf(bimg, sw128(n * 128 + k * 2), B[n * K + k]);
+        p.nk = 4; p.idesc = make_idesc(M, N, 1, 0, 1);
+        for (int s = 0; s < 4; ++s) {
+            p.adesc[s] = variant == 0 ? make_desc(s * 1024, 4096, 512, 4) : make_desc(s * 1024, 512, 4096, 4);
+            p.bdesc[s] = make_desc(s * 32, 16, 1024, 2);
+        }
+        return run_mma_test(variant == 0 ? "T7 A=MN/SW64 (LBO=group 4096, SBO=kgroup 512), B=K/SW128" : "T7' (LBO/SBO swapped)", M, N, K, A, B, aimg, bimg, p, 2e-3);
+    }
     if (test == 5) {
-        // TMA: bf16 tensor (T = 64*16 rows, D = 64), view {d, n, m1} with t = 16*m1 + n; box {32, 2, 64}, SWIZZLE_128B
+        // TMA landing layout: bf16 tensor (T = 64*16 rows, D = 64), t = 16*m1 + n.  The whole 32 KB buffer is dumped and every
+        // element is searched for, so the landing rule is measured instead of assumed.
+        //   variant 0: dims {d, n, m1}, box {32, 2, 64}, SWIZZLE_128B (inner 64 B < span)     1: same, SWIZZLE_NONE
+        //   variant 2: dims {d, m1, n}, box {32, 64, 4}, SWIZZLE_64B  (inner 64 B = span)     3: dims {d, n, m1}, box {64, 1, 64}, SWIZZLE_128B (inner 128 B)
         const int N2 = 16, T = 64 * N2, D = 64;
         std::vector<uint16_t> x((size_t)T * D);
-        for (int t = 0; t < T; ++t) for (int d = 0; d < D; ++d) x[(size_t)t * D + d] = (uint16_t)(t * 64 + d);   // unique tags
+        for (int t = 0; t < T; ++t) for (int d = 0; d < D; ++d) x[(size_t)t * D + d] = (uint16_t)(t * 64 + d);   // unique tags (< 0xFFFF)
         uint16_t* dx; unsigned char* dout;
-        CK(cudaMalloc(&dx, x.size() * 2)); CK(cudaMalloc(&dout, 8192));
+        CK(cudaMalloc(&dx, x.size() * 2)); CK(cudaMalloc(&dout, 32768));
         CK(cudaMemcpy(dx, x.data(), x.size() * 2, cudaMemcpyHostToDevice));
         void* fp = nullptr; cudaDriverEntryPointQueryResult q;
         CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
@@ -293,26 +322,53 @@ int main(int argc, char** argv) {
         cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)N2, 64};
         cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)N2 * D * 2};
         cuuint32_t box[3] = {32, 2, 64}, es[3] = {1, 1, 1};
-        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dx, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { printf("T5: encode failed %d\n", (int)r); return 1; }
-        const int n0 = 6;
-        CK(cudaFuncSetAttribute(tma_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 + 1024));
-        tma_dump_kernel<<<1, 128, 8192 + 1024>>>(tm, dout, n0);
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { printf("T5: KERNEL FAILED: %s\n", cudaGetErrorString(e)); return 1; }
-        std::vector<unsigned char> img(8192);
-        CK(cudaMemcpy(img.data(), dout, 8192, cudaMemcpyDeviceToHost));
-        int bad = 0;
-        for (int m1 = 0; m1 < 64; ++m1) for (int nl = 0; nl < 2; ++nl) for (int d = 0; d < 32; ++d) {
-            const uint32_t off = sw128(m1 * 128 + nl * 64 + d * 2);
-            uint16_t got; memcpy(&got, &img[off], 2);
-            const int t = N2 * m1 + n0 + nl;
-            const uint16_t want = (uint16_t)(t * 64 + 32 + d);
-            if (got != want) { if (bad < 4) printf("T5: (m1=%d n=%d d=%d) at %u: got %u want %u\n", m1, nl, d, off, got, want); ++bad; }
+        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
+        int c1 = 6, c2 = 0, d0 = 32;
+        if (variant == 1) swz = CU_TENSOR_MAP_SWIZZLE_NONE;
+        if (variant == 2) {
+            dims[1] = 64; dims[2] = N2; strides[0] = (cuuint64_t)N2 * D * 2; strides[1] = (cuuint64_t)D * 2;
+            box[1] = 64; box[2] = 4; swz = CU_TENSOR_MAP_SWIZZLE_64B; c1 = 0; c2 = 4;
         }
-        printf("T5 TMA box {32 d, 2 n, 64 m1} SWIZZLE_128B -> [m1][n][d] image with chunk ^= (row & 7): %d mismatches%s\n", bad, bad ? "  -> MISMATCH" : "  -> OK");
-        return bad != 0;
+        if (variant == 3) { box[0] = 64; box[1] = 1; d0 = 0; }
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dx, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("T5: encode failed %d\n", (int)r); return 1; }
+        const int bytes = (int)(box[0] * box[1] * box[2] * 2);
+        CK(cudaFuncSetAttribute(tma_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 1024));
+        tma_dump_kernel<<<1, 128, 32768 + 1024>>>(tm, dout, d0, c1, c2, bytes);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("T5 variant %d: KERNEL FAILED: %s\n", variant, cudaGetErrorString(e)); return 1; }
+        std::vector<unsigned char> img(32768);
+        CK(cudaMemcpy(img.data(), dout, 32768, cudaMemcpyDeviceToHost));
+        // where did each tag land?
+        std::vector<int> where(65536, -1);
+        int landed = 0, maxoff = 0;
+        for (int off = 0; off < 32768; off += 2) {
+            uint16_t v; memcpy(&v, &img[off], 2);
+            if (v != 0xFFFF) { where[v] = off; ++landed; if (off > maxoff) maxoff = off; }
+        }
+        printf("T5 variant %d: %d elements landed (expected %d), highest byte offset %d\n", variant, landed, bytes / 2, maxoff);
+        // hypotheses for the byte offset of (i2, i1, d) = box coordinates (outer, middle, inner)
+        const int nb1 = box[1], nb2 = box[2], nb0 = box[0];
+        int bad_lin = 0, bad_sw128 = 0, bad_sw64 = 0, bad_pad128 = 0, shown = 0;
+        for (int i2 = 0; i2 < nb2; ++i2) for (int i1 = 0; i1 < nb1; ++i1) for (int d = 0; d < nb0; ++d) {
+            int t, dd;
+            if (variant == 2) { t = N2 * i1 + (c2 + i2); dd = 32 + d; }          // {d, m1, n}: i1 = m1, i2 = n
+            else { t = N2 * i2 + (c1 + i1); dd = (variant == 3 ? 0 : 32) + d; }   // {d, n, m1}: i1 = n, i2 = m1
+            const int tag = t * 64 + dd;
+            const int got = where[tag];
+            const uint32_t lin = (uint32_t)((i2 * nb1 + i1) * nb0 + d) * 2;
+            const uint32_t sw64 = lin ^ (((lin >> 7) & 3u) << 4);
+            const uint32_t padlin = (uint32_t)(i2 * nb1 + i1) * 128 + d * 2;
+            if (got != (int)lin) ++bad_lin;
+            if (got != (int)sw128(lin)) ++bad_sw128;
+            if (got != (int)sw64) ++bad_sw64;
+            if (got != (int)sw128(padlin)) ++bad_pad128;
+            if (shown < 12 && (d % 8) == 0 && i2 < 2) { printf("   (i2=%d i1=%d d=%d) lin %u -> landed at %d\n", i2, i1, d, lin, got); ++shown; }
+        }
+        printf("   mismatches vs: linear %d | Swizzle<3,4,3>(linear) %d | Swizzle<2,4,3>(linear) %d | Swizzle<3,4,3>(rows padded to 128 B) %d\n",
+               bad_lin, bad_sw128, bad_sw64, bad_pad128);
+        return 0;
     }
     if (test == 6) {
         // fp32 accumulation in the tensor core: D[128 x 16] over 64 accumulating tf32 MMAs (K = 8 each); values exactly representable in
