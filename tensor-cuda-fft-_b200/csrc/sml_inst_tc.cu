@@ -148,13 +148,29 @@ bool tc_eligible(int T, int D, int k, int io_dtype) {
     return io_dtype == SML_DTYPE_BF16 && D % 32 == 0 && T % 512 == 0 && T >= 512 && T <= 16384 && k >= 1 && k <= 512 && k <= T / 2;
 }
 
+template <bool BWD, bool DUMP>
+int launch_tc_inst(const CUtensorMap& map_in, const sml::TcParams& prm, int grid, size_t smem_bytes, cudaStream_t stream) {
+    auto kern = sml::sml_tc_kernel<BWD, DUMP>;
+    static std::atomic<unsigned long long> attr_done{0};   // per kernel instantiation: one bit per device ordinal
+    int dev = 0;
+    SML_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+        SML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done.fetch_or(bit, std::memory_order_release);
+    }
+    kern<<<grid, sml::tc::THREADS, smem_bytes, stream>>>(map_in, prm);
+    count_launch();
+    SML_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <bool BWD>
 int launch_tc(const void* in, void* out, const TcLaunch& a, int sm_count, cudaStream_t stream) {
     TcTables tabs;
     if (tc_tables(a.T, stream, &tabs)) return 1;
-    CUtensorMap map_in, map_out;
+    CUtensorMap map_in;
     if (encode_tc_map(&map_in, in, a.B, a.T, a.D, true)) return 1;
-    if (encode_tc_map(&map_out, out, a.B, a.T, a.D, false)) return 1;
     sml::TcParams prm{};
     prm.w_re = a.w_re; prm.w_im = a.w_im; prm.bias = a.bias;
     prm.xlow = a.xlow; prm.gw_re = a.gw_re; prm.gpart = a.gpart; prm.gbpart = a.gbpart;
@@ -163,38 +179,32 @@ int launch_tc(const void* in, void* out, const TcLaunch& a, int sm_count, cudaSt
     prm.N2 = a.T / 64;
     prm.ntd = a.D / 32;
     prm.nitems = a.B * prm.ntd;
+    prm.out = out;
     prm.invT = 1.0f / (float)a.T;
     prm.dbg = a.dbg;
+    // as many x-tile landing slots as fit into 227 KB of shared memory (the analysis phase is TMA-latency bound)
+    const uint32_t fixed = sml::tc::smem_map(prm.N2, 0).total;
+    int nslot = (int)((227u * 1024u - fixed) / (16384u + 1024u));
+    if (nslot > sml::tc::MAX_SLOT) nslot = sml::tc::MAX_SLOT;
+    if (nslot < 4) return fail("internal: tensor-core path without room for its x tiles (T=%d)", a.T);
+    prm.nslot = nslot;
+    const size_t smem_bytes = sml::tc::smem_map(prm.N2, nslot).total;
+    const int grid = prm.nitems < sm_count ? prm.nitems : sm_count;
     // bring-up aid: SML_TC_DUMP=<file> writes the intermediates of work item 0 of a FORWARD launch (tools/tc_dump_check.py)
     static const char* dump_path = getenv("SML_TC_DUMP");
-    const size_t dump_floats = (size_t)prm.N2 * 2048 * 2 + 2 * 36864;
     if (dump_path != nullptr && !BWD) {
+        const size_t dump_floats = (size_t)prm.N2 * 2048 * 2 + 2 * 36864;
         SML_CUDA(cudaMalloc(&prm.dump, dump_floats * sizeof(float)));
         SML_CUDA(cudaMemset(prm.dump, 0, dump_floats * sizeof(float)));
-    }
-    auto kern = sml::sml_tc_kernel<BWD>;
-    static std::atomic<unsigned long long> attr_done{0};
-    {
-        int dev = 0;
-        SML_CUDA(cudaGetDevice(&dev));
-        const unsigned long long bit = 1ull << (dev & 63);
-        if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-            SML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml::tc::SMEM_BYTES));
-            attr_done.fetch_or(bit, std::memory_order_release);
-        }
-    }
-    const int grid = prm.nitems < sm_count ? prm.nitems : sm_count;
-    kern<<<grid, sml::tc::THREADS, sml::tc::SMEM_BYTES, stream>>>(map_in, map_out, prm);
-    count_launch();
-    SML_CUDA(cudaGetLastError());
-    if (prm.dump != nullptr) {
+        if (launch_tc_inst<BWD, true>(map_in, prm, grid, smem_bytes, stream)) return 1;
         SML_CUDA(cudaStreamSynchronize(stream));
         std::vector<float> host(dump_floats);
         SML_CUDA(cudaMemcpy(host.data(), prm.dump, dump_floats * sizeof(float), cudaMemcpyDeviceToHost));
         if (FILE* f = fopen(dump_path, "wb")) { fwrite(host.data(), sizeof(float), dump_floats, f); fclose(f); }
         cudaFree(prm.dump);
+        return 0;
     }
-    return 0;
+    return launch_tc_inst<BWD, false>(map_in, prm, grid, smem_bytes, stream);
 }
 
 template int launch_tc<false>(const void*, void*, const TcLaunch&, int, cudaStream_t);

@@ -52,6 +52,8 @@ struct TcParams {
     int N2;                // T / 64
     int ntd;               // channel tiles = D / 32
     int nitems;            // B * ntd
+    int nslot;             // x-tile landing slots (4..8): as many as shared memory allows, the analysis phase is TMA-latency bound
+    void* out;             // y (FWD) / gx (BWD): (B,T,D) bf16, written with plain global stores
     float invT;
     unsigned int* dbg;
     float* dump;           // bring-up aid (SML_TC_DUMP): intermediates of work item 0, see tools/tc_dump_check.py; null in production
@@ -65,23 +67,33 @@ constexpr int ROWS = 32 * RPD;           // 1088 live rows
 constexpr int NTILE = 9;                 // 128-row tiles of the band operand
 constexpr uint32_t PLANE = 1152u * 16u;  // one 8-element k-chunk of all 9 tiles: row * 16 B
 
-// shared-memory map (bytes).  Synthesis re-uses the analysis buffers: band operand <-> A2 chunks, stage-B operand <-> x tiles.
-constexpr uint32_t OFF_B1 = 0;                         // 8 KB
-constexpr uint32_t OFF_B2 = 8192;                      // up to 32 KB (N2 <= 256)
-constexpr uint32_t OFF_X = OFF_B2 + 32768;             // 4 x 16 KB x tiles   | 2 x 32 KB stage-B operand chunks
-constexpr uint32_t OFF_A2 = OFF_X + 65536;             // 2 x 36 KB A2 chunks | 72 KB band operand
-constexpr uint32_t OFF_TW = OFF_A2 + 4 * PLANE;        // 4 x 1 KB twiddle rows of the x tiles
-constexpr uint32_t OFF_TWS = OFF_TW + 4096;            // 2 x 2 KB twiddle rows of the synthesis chunks
-constexpr uint32_t OFF_ST = OFF_TWS + 4096;            // 2 x 16 KB output staging tiles
-constexpr uint32_t OFF_BAR = OFF_ST + 32768;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 512;
+// shared-memory map (bytes; the sizes depend on N2 and on the number of x-tile slots, so the offsets are computed at run time).
+// Synthesis re-uses the analysis buffers: band operand <-> A2 chunks, stage-B operand (2 x 32 KB) <-> x tiles.
+//   B1 8 KB | B2 NA*4 KB | x tiles nslot*16 KB | A2 chunks 2 x 36 KB | twiddle rows nslot*1 KB | synthesis twiddle rows 2 x 2 KB | barriers
+constexpr int MAX_SLOT = 8;
+constexpr uint32_t OFF_B1 = 0;
+constexpr uint32_t OFF_B2 = 8192;
+struct SmemMap {
+    uint32_t x, a2, tw, tws, bar, total;
+};
+__host__ __device__ inline SmemMap smem_map(int N2, int nslot) {
+    SmemMap m;
+    m.x = OFF_B2 + (uint32_t)((N2 + 31) / 32) * 4096u;
+    m.a2 = m.x + (uint32_t)nslot * 16384u;
+    m.tw = m.a2 + 4u * PLANE;
+    m.tws = m.tw + (uint32_t)nslot * 1024u;
+    m.bar = m.tws + 4096u;
+    m.total = m.bar + 1024u;
+    return m;
+}
 
 struct Bars {
-    uint64_t x_full[4], x_free[4], d1_full[2], d1_free[2], a2_full[2], a2_free[2], d2_full, aband_full;
+    uint64_t x_full[MAX_SLOT], x_free[MAX_SLOT], d1_full[2], d1_free[2], a2_full[2], a2_free[2], d2_full, aband_full;
     uint64_t tws_full[2], tws_free[2], da_full[2], da_free[2], ab_full[2], ab_free[2], db_full[2], db_free[2];
+    uint64_t xregion_free;   // once per work item: the last stage-B MMAs have read the x-tile region (it doubles as their operand)
     uint32_t tmem_base;
 };
-static_assert(sizeof(Bars) <= 512, "barrier block");
+static_assert(sizeof(Bars) <= 1024, "barrier block");
 
 // TMEM columns
 constexpr uint32_t COL_D1 = 0;      // 2 x 64 (stage 1) | 2 x 64 (stage B)
@@ -117,6 +129,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void stg_bf16(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -136,6 +149,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
+// mbarrier wait for the tensor-core kernel: the try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware
+// instead of burning issue slots in a poll loop (the compute warps share their schedulers with the warps that are working);
+// bounded like mbar_wait (10 s of %globaltimer), a lost arrival traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_tc(uint64_t* bar, uint32_t parity, unsigned int* dbg, uint32_t tag, uint32_t aux) {
+    uint64_t t0 = 0;
+    for (uint32_t spins = 1;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+        if (ok) return;
+        if ((spins & 0xFFu) == 0u) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ull) mbar_timeout(dbg, tag, parity, aux);
+        }
+    }
+}
 // warp-level arrive: every lane has finished its part (and fenced it) before lane 0 signals
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
     __syncwarp();
@@ -143,82 +175,74 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// mid phase for one band row (channel d, row class p): in = the 16 two-sided accumulator slots Z[q], f2 = q - 8;
+// mid phase for one band row (channel d, class f1 = 0..32): in = the 16 two-sided accumulator slots Z[q], f2 = q - 8;
 // out = the 16 band slots of the synthesis operand as packed bf16 (re, im).
+//   slot q >= 8 holds the bin f = f1 + 64 (q - 8):                X_f = Z[q]
+//   slot q <  8 holds the NEGATIVE frequency f1 + 64 (q - 8):     X_f = conj Z[q] for the bin f = 64 (8 - q) - f1
+// Classes 0 and 32 are self-conjugate (every bin shows up on both sides, half weight each); the DC bin carries the bias.
+// All filter / X_low loads of eight slots are issued before the first use, so their latencies overlap.
 // ------------------------------------------------------------------------------------------------
 template <bool BWD>
-__device__ __forceinline__ void mid_row(const uint32_t (&z)[32], uint32_t (&outw)[16], const TcParams& prm, int b, int d, int p) {
+__device__ __forceinline__ void mid_row(const uint32_t (&z)[32], uint32_t (&outw)[16], const TcParams& prm, int b, int d, int f1) {
     const int k = prm.k;
     const float invT = prm.invT;
-    const size_t wrow = (size_t)d * prm.F;
-    const size_t xrow = ((size_t)b * prm.D + d) * (size_t)k;
+    const bool selfconj = f1 == 0 || f1 == 32;
+    const float scale = selfconj ? 0.5f * invT : invT;
     const bool grads = BWD && prm.gw_re != nullptr;
+    const float* const wre = prm.w_re + (size_t)d * prm.F;
+    const float* const wim = prm.w_im + (size_t)d * prm.F;
+    const size_t xrow = ((size_t)b * prm.D + d) * (size_t)k;
+    float2* const xl = reinterpret_cast<float2*>(prm.xlow) + xrow;
+    float2* const gp = reinterpret_cast<float2*>(prm.gpart) + xrow;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) outw[q] = 0u;
-    // one live bin f whose spectrum value is X (already conjugated for a negative-side slot); returns A = X W (FWD) or G conj(W) (BWD)
-    auto bin = [&](int f, cf X, float scale) -> cf {
-        const cf w = cf{__ldg(prm.w_re + wrow + f), __ldg(prm.w_im + wrow + f)};
-        cf a;
-        if constexpr (!BWD) {
-            if (prm.xlow != nullptr) reinterpret_cast<float2*>(prm.xlow)[xrow + f] = make_float2(X.re, X.im);
-            a = cmul(X, w);
-        } else {
-            if (grads) {
-                const float2 xs = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow + f);
-                const cf gt = cmulc(X, cf{xs.x, xs.y});   // G conj(X_low), wirtinger_ops.py:77
-                reinterpret_cast<float2*>(prm.gpart)[xrow + f] = make_float2(gt.re * invT, gt.im * invT);
-                if (f == 0) prm.gbpart[(size_t)b * prm.D + d] = X.re;
-            }
-            a = cmulc(X, w);
-        }
-        return cf{a.re * scale, a.im * scale};
-    };
-    auto Z = [&](int q) -> cf { return cf{__uint_as_float(z[2 * q]), __uint_as_float(z[2 * q + 1])}; };
-    if (p >= 2 && p <= 32) {              // classes f1 = 1..31: bins f1 + 64 f2 on the positive side, 64 f2' - f1 on the negative side
-        const int f1 = p - 1;
+    for (int half = 0; half < 2; ++half) {
+        float wr[8], wi[8];
+        float2 xs[8];
+        int fq[8];
 #pragma unroll
-        for (int f2 = 0; f2 < 8; ++f2) {
-            const int f = f1 + 64 * f2;
-            if (f < k) {
-                const cf a = bin(f, Z(8 + f2), invT);
-                outw[8 + f2] = pack_bf16(a.re, a.im);
+        for (int j = 0; j < 8; ++j) {
+            const int q = 8 * half + j;
+            const int f = q >= 8 ? f1 + 64 * (q - 8) : 64 * (8 - q) - f1;
+            fq[j] = f < k ? f : -1;
+            wr[j] = 0.f; wi[j] = 0.f; xs[j] = make_float2(0.f, 0.f);
+            if (fq[j] >= 0) {
+                wr[j] = __ldg(wre + f);
+                wi[j] = __ldg(wim + f);
+                if (grads) xs[j] = __ldg(xl + f);
             }
         }
 #pragma unroll
-        for (int g2 = 1; g2 <= 8; ++g2) {
-            const int f = 64 * g2 - f1;
-            if (f < k) {
-                const cf zc = Z(8 - g2);
-                const cf a = bin(f, cf{zc.re, -zc.im}, invT);
-                outw[8 - g2] = pack_bf16(a.re, -a.im);
+        for (int j = 0; j < 8; ++j) {
+            const int q = 8 * half + j;
+            const bool neg = q < 8;
+            const float zr = __uint_as_float(z[2 * q]), zi = __uint_as_float(z[2 * q + 1]);
+            const cf X = cf{zr, neg ? -zi : zi};
+            uint32_t o = 0u;
+            if (fq[j] >= 0) {
+                const bool owner = !(selfconj && neg);   // a self-conjugate class sees each bin twice: the positive side writes it
+                cf a;
+                if constexpr (!BWD) {
+                    if (owner && prm.xlow != nullptr) xl[fq[j]] = make_float2(X.re, X.im);
+                    a = cmul(X, cf{wr[j], wi[j]});
+                } else {
+                    if (grads && owner) {
+                        const cf gt = cmulc(X, cf{xs[j].x, xs[j].y});   // G conj(X_low), wirtinger_ops.py:77
+                        gp[fq[j]] = make_float2(gt.re * invT, gt.im * invT);
+                        if (fq[j] == 0) prm.gbpart[(size_t)b * prm.D + d] = X.re;
+                    }
+                    a = cmulc(X, cf{wr[j], wi[j]});
+                }
+                float ore = a.re * scale, oim = (neg ? -a.im : a.im) * scale;
+                if (f1 == 0 && q == 8) {          // DC: full weight, real, + bias (a constant in time)
+                    ore = a.re * invT;
+                    oim = 0.f;
+                    if constexpr (!BWD) {
+                        if (prm.bias != nullptr) ore += __ldg(prm.bias + d);
+                    }
+                }
+                o = pack_bf16(ore, oim);
             }
-        }
-    } else if (p == 0) {                  // class 0: bins 64 f2; the DC bin carries the bias (a constant in time)
-        {
-            cf a = bin(0, Z(8), invT);
-            if constexpr (!BWD) {
-                if (prm.bias != nullptr) a.re += __ldg(prm.bias + d);
-            }
-            outw[8] = pack_bf16(a.re, 0.f);
-        }
-#pragma unroll
-        for (int f2 = 1; f2 < 8; ++f2) {
-            const int f = 64 * f2;
-            if (f < k) {
-                const cf a = bin(f, Z(8 + f2), 0.5f * invT);
-                outw[8 + f2] = pack_bf16(a.re, a.im);
-                outw[8 - f2] = pack_bf16(a.re, -a.im);
-            }
-        }
-    } else if (p == 1) {                  // class 32: bins 32 + 64 f2; their mirrors -(32 + 64 f2) = 32 + 64 (-f2 - 1)
-#pragma unroll
-        for (int f2 = 0; f2 < 8; ++f2) {
-            const int f = 32 + 64 * f2;
-            if (f < k) {
-                const cf a = bin(f, Z(8 + f2), 0.5f * invT);
-                outw[8 + f2] = pack_bf16(a.re, a.im);
-                outw[7 - f2] = pack_bf16(a.re, -a.im);
-            }
+            outw[q] = o;
         }
     }
 }
@@ -228,21 +252,23 @@ __device__ __forceinline__ void mid_row(const uint32_t (&z)[32], uint32_t (&outw
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <bool BWD>
+template <bool BWD, bool DUMP>
 __global__ void __launch_bounds__(tc::THREADS, 1)
-    sml_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out, const TcParams prm) {
+    sml_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams prm) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem[];
-    Bars* const bars = reinterpret_cast<Bars*>(smem + OFF_BAR);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N2 = prm.N2;
+    const int nslot = prm.nslot;
+    const SmemMap sm = smem_map(N2, nslot);
+    Bars* const bars = reinterpret_cast<Bars*>(smem + sm.bar);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NT1 = N2 >> 2;   // stage-1 / stage-B tiles (4 n each) per work item: even
     const int NCH = N2 >> 3;   // stage-2 / stage-A chunks (8 n each)
     unsigned int* const dbg = prm.dbg;
 
     // ---- one-time setup: barriers, TMEM, resident tables ----
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_free[i], 9); }
+        for (int i = 0; i < MAX_SLOT; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_free[i], 9); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->d1_full[i], 1);  mbar_init(&bars->d1_free[i], 8);
             mbar_init(&bars->a2_full[i], 16); mbar_init(&bars->a2_free[i], 1);
@@ -253,6 +279,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
         }
         mbar_init(&bars->d2_full, 1);
         mbar_init(&bars->aband_full, 16);
+        mbar_init(&bars->xregion_free, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -268,7 +295,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
         uint4* d2 = reinterpret_cast<uint4*>(smem + OFF_B2);
         for (int i = tid; i < nb2; i += THREADS) d2[i] = __ldg(s2 + i);
         // rows >= ROWS of the band operand are read by the last tile's MMAs: keep them finite
-        uint4* za = reinterpret_cast<uint4*>(smem + OFF_A2);
+        uint4* za = reinterpret_cast<uint4*>(smem + sm.a2);
         for (int i = tid; i < (int)(4 * PLANE / 16); i += THREADS) za[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     fence_proxy_async();
@@ -290,6 +317,24 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
     const int wg = cw >> 2;              // warpgroup 0..3
     const int quad = warp & 3;           // TMEM lane quadrant of this warp
     const uint32_t tq = tmem + ((uint32_t)(quad * 32) << 16);
+    const int tp = wg >> 1, h = wg & 1;  // tile parity and column half for the per-tile epilogues
+
+    // x-tile slot rings: every role walks the same sequence of (slot, phase); the epilogue pairs take every second tile
+    int xs = warp >= 4 ? tp : 0;         // slot of this role's next tile
+    uint32_t xph = 0;                    // its phase bit
+    auto xadvance = [&](int step) {
+        xs += step;
+        if (xs >= nslot) { xs -= nslot; xph ^= 1u; }
+    };
+    int prefetched = 0;                  // producer: tiles of the CURRENT item already issued at the end of the previous one
+
+    auto issue_x = [&](int b_, int d0_, int i) {   // producer thread: tile i of work item (b_, d0_) into the next slot
+        mbar_wait_tc(&bars->x_free[xs], xph ^ 1u, dbg, 1u, (uint32_t)i);
+        mbar_expect_tx(&bars->x_full[xs], 16384u + 1024u);
+        tma_load_4d(smem + sm.x + (uint32_t)xs * 16384u, &tmap_in, &bars->x_full[xs], d0_, 0, 4 * i, b_);   // box {32 d, 64 m1, 4 n}: [n][m1][d], SWIZZLE_64B
+        bulk_g2s(smem + sm.tw + (uint32_t)xs * 1024u, prm.tw + (size_t)(4 * i) * 32, 1024u, &bars->x_full[xs]);
+        xadvance(1);
+    };
 
     for (int it = 0; it < my_items; ++it) {
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
@@ -301,19 +346,25 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
         if (warp == 0) {
             // =========================== TMA producer ===========================
             if (lane == 0) {
-                for (int i = 0; i < NT1; ++i) {
-                    const uint32_t u = gi0 + i, s = u & 3u;
-                    mbar_wait(&bars->x_free[s], ((u >> 2) & 1u) ^ 1u, dbg, 1u, u);
-                    mbar_expect_tx(&bars->x_full[s], 16384u + 1024u);
-                    unsigned char* xt = smem + OFF_X + s * 16384u;
-                    tma_load_4d(xt, &tmap_in, &bars->x_full[s], d0, 0, 4 * i, b);   // box {32 d, 64 m1, 4 n}: [n][m1][d], SWIZZLE_64B
-                    bulk_g2s(smem + OFF_TW + s * 1024u, prm.tw + (size_t)(4 * i) * 32, 1024u, &bars->x_full[s]);
-                }
+                for (int i = prefetched; i < NT1; ++i) issue_x(b, d0, i);
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t u = gc0 + c, s = u & 1u;
-                    mbar_wait(&bars->tws_free[s], ((u >> 1) & 1u) ^ 1u, dbg, 2u, u);
+                    mbar_wait_tc(&bars->tws_free[s], ((u >> 1) & 1u) ^ 1u, dbg, 2u, u);
                     mbar_expect_tx(&bars->tws_full[s], 2048u);
-                    bulk_g2s(smem + OFF_TWS + s * 2048u, prm.tw + (size_t)(8 * c) * 32, 2048u, &bars->tws_full[s]);
+                    bulk_g2s(smem + sm.tws + s * 2048u, prm.tw + (size_t)(8 * c) * 32, 2048u, &bars->tws_full[s]);
+                }
+                // the x-tile region doubles as the stage-B operand: once the last stage-B MMAs have read it, the first tiles of the
+                // NEXT work item can land while this item's last outputs are still being written
+                prefetched = 0;
+                if (it + 1 < my_items) {
+                    // (a barrier of its own, one phase per work item: this thread is many phases behind ab_free, and a parity
+                    //  wait cannot tell phase j from phase j - 2)
+                    mbar_wait_tc(&bars->xregion_free, (uint32_t)it & 1u, dbg, 19u, (uint32_t)it);
+                    const int item2 = item + (int)gridDim.x;
+                    const int b2 = item2 / prm.ntd, d02 = (item2 - b2 * prm.ntd) * 32;
+                    const int npre = nslot < NT1 ? nslot : NT1;
+                    for (int i = 0; i < npre; ++i) issue_x(b2, d02, i);
+                    prefetched = npre;
                 }
             }
         } else if (warp == 1) {
@@ -321,31 +372,32 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
             if (lane == 0) {
                 auto stage2 = [&](int c) {
                     const uint32_t uc = gc0 + c, s2 = uc & 1u;
-                    mbar_wait(&bars->a2_full[s2], (uc >> 1) & 1u, dbg, 3u, uc);
+                    mbar_wait_tc(&bars->a2_full[s2], (uc >> 1) & 1u, dbg, 3u, uc);
                     tc_fence_after();
                     const uint64_t bd = smem_desc(sbase + OFF_B2 + (uint32_t)(c >> 2) * 4096u + (uint32_t)(c & 3) * 32u, 16, 1024, LAYOUT_SW128);
 #pragma unroll 1
                     for (int t = 0; t < NTILE; ++t) {
-                        const uint64_t ad = smem_desc(sbase + OFF_A2 + s2 * 2u * PLANE + (uint32_t)t * 2048u, PLANE, 128, LAYOUT_NONE);
+                        const uint64_t ad = smem_desc(sbase + sm.a2 + s2 * 2u * PLANE + (uint32_t)t * 2048u, PLANE, 128, LAYOUT_NONE);
                         mma_bf16(tmem + COL_D2 + 32u * t, ad, bd, IDESC_S2, c > 0 ? 1u : 0u);
                     }
                     mma_commit(&bars->a2_free[s2]);
                 };
                 // ---- analysis ----
                 for (int i = 0; i < NT1; ++i) {
-                    const uint32_t u = gi0 + i, s = u & 3u, p = u & 1u;
-                    mbar_wait(&bars->x_full[s], (u >> 2) & 1u, dbg, 4u, u);
-                    mbar_wait(&bars->d1_free[p], ((u >> 1) & 1u) ^ 1u, dbg, 5u, u);
+                    const uint32_t u = gi0 + i, p = u & 1u;
+                    mbar_wait_tc(&bars->x_full[xs], xph, dbg, 4u, u);
+                    mbar_wait_tc(&bars->d1_free[p], ((u >> 1) & 1u) ^ 1u, dbg, 5u, u);
                     tc_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         // MN-major SWIZZLE_64B: 32 channels (64 B) contiguous, 8 k-rows (m1) at 64 B, one MN group per n
-                        const uint64_t ad = smem_desc(sbase + OFF_X + s * 16384u + ks * 1024u, 4096, 512, LAYOUT_SW64);
+                        const uint64_t ad = smem_desc(sbase + sm.x + (uint32_t)xs * 16384u + ks * 1024u, 4096, 512, LAYOUT_SW64);
                         const uint64_t bd = smem_desc(sbase + OFF_B1 + ks * 32u, 16, 1024, LAYOUT_SW128);
                         mma_bf16(tmem + COL_D1 + 64u * p, ad, bd, IDESC_S1, ks > 0 ? 1u : 0u);
                     }
-                    mma_commit(&bars->x_free[s]);
+                    mma_commit(&bars->x_free[xs]);
                     mma_commit(&bars->d1_full[p]);
+                    xadvance(1);
                     if ((i & 1) && i >= 3) stage2((i - 3) >> 1);
                 }
                 stage2(NCH - 1);
@@ -353,13 +405,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 // ---- synthesis ----
                 auto stageA = [&](int c) {
                     const uint32_t uc = gc0 + c, s = uc & 1u;
-                    mbar_wait(&bars->da_free[s], ((uc >> 1) & 1u) ^ 1u, dbg, 6u, uc);
+                    mbar_wait_tc(&bars->da_free[s], ((uc >> 1) & 1u) ^ 1u, dbg, 6u, uc);
                     tc_fence_after();
 #pragma unroll 1
                     for (int t = 0; t < NTILE; ++t) {
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
-                            const uint64_t ad = smem_desc(sbase + OFF_A2 + (uint32_t)t * 2048u + ks * 2u * PLANE, PLANE, 128, LAYOUT_NONE);
+                            const uint64_t ad = smem_desc(sbase + sm.a2 + (uint32_t)t * 2048u + ks * 2u * PLANE, PLANE, 128, LAYOUT_NONE);
                             const uint64_t bd = smem_desc(sbase + OFF_B2 + (uint32_t)(c >> 2) * 4096u + ks * 2048u + (uint32_t)(c & 3) * 32u, 0, 1024, LAYOUT_SW128);
                             mma_bf16(tmem + COL_D2 + s * 144u + 16u * t, ad, bd, IDESC_SA, ks > 0 ? 1u : 0u);
                         }
@@ -370,18 +422,18 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                     const uint32_t u = gi0 + i, p = u & 1u;
                     const int c = i >> 1;
                     const uint32_t uc = gc0 + c, s = uc & 1u;
-                    if ((i & 1) == 0) mbar_wait(&bars->ab_full[s], (uc >> 1) & 1u, dbg, 7u, uc);
-                    mbar_wait(&bars->db_free[p], ((u >> 1) & 1u) ^ 1u, dbg, 8u, u);
+                    if ((i & 1) == 0) mbar_wait_tc(&bars->ab_full[s], (uc >> 1) & 1u, dbg, 7u, uc);
+                    mbar_wait_tc(&bars->db_free[p], ((u >> 1) & 1u) ^ 1u, dbg, 8u, u);
                     tc_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t ad = smem_desc(sbase + OFF_X + s * 32768u + (uint32_t)(i & 1) * 16384u + ks * 32u, 16, 1024, LAYOUT_SW128);
+                        const uint64_t ad = smem_desc(sbase + sm.x + s * 32768u + (uint32_t)(i & 1) * 16384u + ks * 32u, 16, 1024, LAYOUT_SW128);
                         const uint64_t bd = smem_desc(sbase + OFF_B1 + ks * 2048u, 0, 1024, LAYOUT_SW128);
                         mma_bf16(tmem + COL_D1 + 64u * p, ad, bd, IDESC_SB, ks > 0 ? 1u : 0u);
                     }
                     mma_commit(&bars->db_full[p]);
                 };
-                mbar_wait(&bars->aband_full, (uint32_t)it & 1u, dbg, 9u, (uint32_t)it);
+                mbar_wait_tc(&bars->aband_full, (uint32_t)it & 1u, dbg, 9u, (uint32_t)it);
                 tc_fence_after();
                 stageA(0);
                 if (NCH > 1) stageA(1);
@@ -391,20 +443,20 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                     mma_commit(&bars->ab_free[(gc0 + c) & 1u]);
                     if (c + 2 < NCH) stageA(c + 2);
                 }
+                mma_commit(&bars->xregion_free);
                 // every MMA of this work item has completed when the last commit has arrived
                 const uint32_t ul = gc0 + NCH - 1;
-                mbar_wait(&bars->ab_free[ul & 1u], (ul >> 1) & 1u, dbg, 10u, ul);
+                mbar_wait_tc(&bars->ab_free[ul & 1u], (ul >> 1) & 1u, dbg, 10u, ul);
             }
         } else if (warp >= 4) {
             // =========================== compute warps ===========================
-            const int tp = wg >> 1, h = wg & 1;   // tile parity and column half for the per-tile epilogues
             // ---- analysis epilogue: stage-1 accumulator -> twiddle -> A2 chunk (transposed) ----
             for (int i = tp; i < NT1; i += 2) {
-                const uint32_t u = gi0 + i, s = u & 3u, p = u & 1u;
-                mbar_wait(&bars->x_full[s], (u >> 2) & 1u, dbg, 11u, u);
+                const uint32_t u = gi0 + i, p = u & 1u;
+                mbar_wait_tc(&bars->x_full[xs], xph, dbg, 11u, u);
                 float2 twv[16];
                 {
-                    const float4* tws = reinterpret_cast<const float4*>(smem + OFF_TW + s * 1024u + quad * 256 + h * 128);
+                    const float4* tws = reinterpret_cast<const float4*>(smem + sm.tw + (uint32_t)xs * 1024u + quad * 256 + h * 128);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 q4 = tws[j];
@@ -412,19 +464,20 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                         twv[2 * j + 1] = make_float2(q4.z, q4.w);
                     }
                 }
-                mbar_wait(&bars->d1_full[p], (u >> 1) & 1u, dbg, 12u, u);
+                mbar_wait_tc(&bars->d1_full[p], (u >> 1) & 1u, dbg, 12u, u);
                 tc_fence_after();
                 uint32_t v[32];
                 tmem_ld32(tq + COL_D1 + 64u * p + 32u * h, v);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&bars->d1_free[p]); mbar_arrive(&bars->x_free[s]); }
+                if (lane == 0) { mbar_arrive(&bars->d1_free[p]); mbar_arrive(&bars->x_free[xs]); }
+                xadvance(2);
                 const int c = i >> 1;
                 const uint32_t uc = gc0 + c, s2 = uc & 1u;
-                mbar_wait(&bars->a2_free[s2], ((uc >> 1) & 1u) ^ 1u, dbg, 13u, uc);
+                mbar_wait_tc(&bars->a2_free[s2], ((uc >> 1) & 1u) ^ 1u, dbg, 13u, uc);
                 // row of (channel lane, class): (lane*34 + p)*16 bytes; k slot of n = 4i + quad inside the chunk: plane i&1, word quad
-                unsigned char* const a2 = smem + OFF_A2 + s2 * 2u * PLANE + (uint32_t)(i & 1) * PLANE + (uint32_t)lane * (RPD * 16) + quad * 4;
+                unsigned char* const a2 = smem + sm.a2 + s2 * 2u * PLANE + (uint32_t)(i & 1) * PLANE + (uint32_t)lane * (RPD * 16) + quad * 4;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float re = __uint_as_float(v[2 * j]), im = __uint_as_float(v[2 * j + 1]);
@@ -432,26 +485,30 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                         // slots 0 / 1 = Re S_0 / Re S_32 (both real): class 0 is not twiddled, class 32 gets W_T^{32 n}
                         *reinterpret_cast<uint32_t*>(a2 + 0 * 16) = pack_bf16(re, 0.f);
                         *reinterpret_cast<uint32_t*>(a2 + 1 * 16) = pack_bf16(im * twv[0].x, im * twv[0].y);
+                        if constexpr (DUMP) {
+                            if (item == 0) {
+                                float* dp = prm.dump + ((size_t)(4 * i + quad) * 32 + lane) * 64;
+                                dp[0] = re; dp[1] = im;
+                            }
+                        }
                     } else {
                         const cf w = cmul(cf{re, im}, cf{twv[j].x, twv[j].y});
                         const int prow = 16 * h + j + 1;   // class f1 = 16h + j sits in row f1 + 1
                         *reinterpret_cast<uint32_t*>(a2 + prow * 16) = pack_bf16(w.re, w.im);
-                        if (prm.dump != nullptr && item == 0) {
-                            float* dp = prm.dump + ((size_t)(4 * i + quad) * 32 + lane) * 64 + 32 * h + 2 * j;
-                            dp[0] = w.re; dp[1] = w.im;
+                        if constexpr (DUMP) {
+                            if (item == 0) {
+                                float* dp = prm.dump + ((size_t)(4 * i + quad) * 32 + lane) * 64 + 32 * h + 2 * j;
+                                dp[0] = w.re; dp[1] = w.im;
+                            }
                         }
                     }
-                }
-                if (prm.dump != nullptr && item == 0 && h == 0) {   // raw stage-1 slots 0 / 1 (Re S_0, Re S_32)
-                    float* dp = prm.dump + ((size_t)(4 * i + quad) * 32 + lane) * 64;
-                    dp[0] = __uint_as_float(v[0]); dp[1] = __uint_as_float(v[1]);
                 }
                 fence_proxy_async();
                 warp_arrive(&bars->a2_full[s2], lane);
             }
 
             // ---- mid phase: band accumulator -> filter -> band operand of the synthesis ----
-            mbar_wait(&bars->d2_full, (uint32_t)it & 1u, dbg, 14u, (uint32_t)it);
+            mbar_wait_tc(&bars->d2_full, (uint32_t)it & 1u, dbg, 14u, (uint32_t)it);
             tc_fence_after();
             for (int t = wg; t < NTILE; t += 4) {
                 const int r = 128 * t + 32 * quad + lane;
@@ -460,24 +517,26 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 tmem_ld_wait();
                 uint32_t outw[16];
                 const int dl = r / RPD, p = r - dl * RPD;
-                if (r < ROWS) {
-                    mid_row<BWD>(z, outw, prm, b, d0 + dl, p);
+                if (r < ROWS && p <= 32) {
+                    mid_row<BWD>(z, outw, prm, b, d0 + dl, p == 0 ? 0 : p == 1 ? 32 : p - 1);
                 } else {
 #pragma unroll
                     for (int q = 0; q < 16; ++q) outw[q] = 0u;
                 }
-                if (prm.dump != nullptr && item == 0) {
-                    float* dz = prm.dump + (size_t)N2 * 2048 + (size_t)r * 32;
-                    float* dbn = prm.dump + (size_t)N2 * 2048 + 36864 + (size_t)r * 32;
+                if constexpr (DUMP) {
+                    if (item == 0) {
+                        float* dz = prm.dump + (size_t)N2 * 2048 + (size_t)r * 32;
+                        float* dbn = prm.dump + (size_t)N2 * 2048 + 36864 + (size_t)r * 32;
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) dz[q] = __uint_as_float(z[q]);
+                        for (int q = 0; q < 32; ++q) dz[q] = __uint_as_float(z[q]);
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&outw[q]);
-                        dbn[2 * q] = __low2float(hh); dbn[2 * q + 1] = __high2float(hh);
+                        for (int q = 0; q < 16; ++q) {
+                            const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&outw[q]);
+                            dbn[2 * q] = __low2float(hh); dbn[2 * q + 1] = __high2float(hh);
+                        }
                     }
                 }
-                unsigned char* const ab = smem + OFF_A2 + (uint32_t)r * 16u;
+                unsigned char* const ab = smem + sm.a2 + (uint32_t)r * 16u;
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl)
                     *reinterpret_cast<uint4*>(ab + pl * PLANE) = make_uint4(outw[4 * pl], outw[4 * pl + 1], outw[4 * pl + 2], outw[4 * pl + 3]);
@@ -489,37 +548,39 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
             // ---- synthesis epilogues, software-pipelined by one chunk: EA(c) then EB(tiles of chunk c-1) ----
             auto epilogueA = [&](int c) {
                 const uint32_t uc = gc0 + c, s = uc & 1u;
-                mbar_wait(&bars->tws_full[s], (uc >> 1) & 1u, dbg, 15u, uc);
-                mbar_wait(&bars->da_full[s], (uc >> 1) & 1u, dbg, 16u, uc);
+                mbar_wait_tc(&bars->tws_full[s], (uc >> 1) & 1u, dbg, 15u, uc);
+                mbar_wait_tc(&bars->da_full[s], (uc >> 1) & 1u, dbg, 16u, uc);
                 tc_fence_after();
-                mbar_wait(&bars->ab_free[s], ((uc >> 1) & 1u) ^ 1u, dbg, 17u, uc);
-                const float2* const twc = reinterpret_cast<const float2*>(smem + OFF_TWS + s * 2048u);
+                mbar_wait_tc(&bars->ab_free[s], ((uc >> 1) & 1u) ^ 1u, dbg, 17u, uc);
+                const float2* const twc = reinterpret_cast<const float2*>(smem + sm.tws + s * 2048u);
                 for (int t = wg; t < NTILE; t += 4) {
                     const int r = 128 * t + 32 * quad + lane;
                     const int dl = r / RPD, p = r - dl * RPD;
                     uint32_t v[16];
                     tmem_ld16(tq + COL_D2 + s * 144u + 16u * t, v);
                     tmem_ld_wait();
-                    const bool live = r < ROWS && p <= 32;
-                    const int jtw = p >= 2 ? p - 1 : 0;                  // twiddle column: class f1 = p - 1; class 32 uses column 0
-                    const int word = p >= 2 ? p - 1 : 0;                 // 4-byte k word of the stage-B operand row: (Re, Im) of class f1
+                    const bool live = r < ROWS && p <= 32 && p != 1;
+                    const int word = p >= 2 ? p - 1 : 0;                 // twiddle column AND 4-byte k word of the stage-B operand row
+                    // row R = (nn & 3) * 32 + dl of tile nn >> 2: byte nn * 4096 + dl * 128; the swizzle term only depends on dl
+                    unsigned char* const dst = smem + sm.x + s * 32768u + (uint32_t)dl * 128u + (uint32_t)(((word >> 2) ^ (dl & 7)) << 4) +
+                                               (uint32_t)(word & 3) * 4u;
+                    const float2* const twp = twc + word;
 #pragma unroll
                     for (int nn = 0; nn < 8; ++nn) {
                         const float yr = __uint_as_float(v[2 * nn]), yi = __uint_as_float(v[2 * nn + 1]);
-                        const float2 w = twc[nn * 32 + jtw];
+                        const float2 w = twp[nn * 32];
                         // Y * conj(W_T^{n f1})
                         float vr = yr * w.x + yi * w.y;
                         float vi = yi * w.x - yr * w.y;
                         if (p == 0) vr = yr;                             // class 0 is not twiddled
                         const float up = __shfl_down_sync(0xffffffffu, vr, 1);   // class 32 (row p = 1) hands Re V_32 to its class-0 neighbour
                         if (p == 0) vi = up;
-                        const int R = (nn & 3) * 32 + dl;
-                        unsigned char* dst = smem + OFF_X + s * 32768u + (uint32_t)(nn >> 2) * 16384u + (uint32_t)R * 128u +
-                                             (uint32_t)(((word >> 2) ^ (R & 7)) << 4) + (uint32_t)(word & 3) * 4u;
-                        if (live && p != 1) *reinterpret_cast<uint32_t*>(dst) = pack_bf16(vr, vi);
-                        if (prm.dump != nullptr && item == 0 && live && p != 1) {
-                            float* dp = prm.dump + (size_t)N2 * 2048 + 2 * 36864 + ((size_t)(8 * c + nn) * 32 + dl) * 64 + 2 * word;
-                            dp[0] = vr; dp[1] = vi;
+                        if (live) *reinterpret_cast<uint32_t*>(dst + nn * 4096) = pack_bf16(vr, vi);
+                        if constexpr (DUMP) {
+                            if (item == 0 && live) {
+                                float* dp = prm.dump + (size_t)N2 * 2048 + 2 * 36864 + ((size_t)(8 * c + nn) * 32 + dl) * 64 + 2 * word;
+                                dp[0] = vr; dp[1] = vi;
+                            }
                         }
                     }
                 }
@@ -528,10 +589,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&bars->ab_full[s]); mbar_arrive(&bars->da_free[s]); mbar_arrive(&bars->tws_free[s]); }
             };
-            const bool store_leader = (cw == 8 * tp) && lane == 0;   // one thread per tile-parity pair of warpgroups issues the TMA stores
+            // stage-B accumulator -> bf16 -> global: thread (n = 4i + quad, d = lane) owns the 32 rows t = N2*m1 + n, m1 = 32h .. 32h+31;
+            // a warp store covers 32 channels = 64 contiguous bytes
+            const size_t row_stride = (size_t)N2 * prm.D;
+            __nv_bfloat16* const obase = reinterpret_cast<__nv_bfloat16*>(prm.out) + ((size_t)b * prm.T + quad) * prm.D + d0 + lane +
+                                         (size_t)(32 * h) * row_stride;
             auto epilogueB = [&](int i) {
                 const uint32_t u = gi0 + i, p = u & 1u;
-                mbar_wait(&bars->db_full[p], (u >> 1) & 1u, dbg, 18u, u);
+                mbar_wait_tc(&bars->db_full[p], (u >> 1) & 1u, dbg, 18u, u);
                 tc_fence_after();
                 uint32_t v[32];
                 tmem_ld32(tq + COL_D1 + 64u * p + 32u * h, v);
@@ -539,19 +604,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->db_free[p]);
-                if (store_leader) tma_store_wait_read();           // the staging tile's previous store has been read out
-                named_bar_sync(1 + tp, 256);
-                // staging tile [4 n][64 m1][32 d] (the store box, no swizzle): this thread owns (n = quad, d = lane)
-                unsigned char* const st = smem + OFF_ST + (uint32_t)tp * 16384u + (uint32_t)quad * 4096u + lane * 2;
+                __nv_bfloat16* o = obase + (size_t)(4 * i) * prm.D;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    *reinterpret_cast<__nv_bfloat16*>(st + (32 * h + j) * 64) = __float2bfloat16_rn(__uint_as_float(v[j]));
-                fence_proxy_async();
-                named_bar_sync(1 + tp, 256);
-                if (store_leader) {
-                    tma_store_4d(&tmap_out, smem + OFF_ST + (uint32_t)tp * 16384u, d0, 0, 4 * i, b);
-                    tma_store_commit();
-                }
+                for (int j = 0; j < 32; ++j) stg_bf16(o + (size_t)j * row_stride, __uint_as_float(v[j]));
             };
             epilogueA(0);
             for (int c = 1; c < NCH; ++c) {
@@ -559,15 +614,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 epilogueB(2 * (c - 1) + tp);
             }
             epilogueB(2 * (NCH - 1) + tp);
-            if (store_leader) tma_store_wait_read();
         }
         // ---- end of the work item: every role has drained; the aliased buffers and TMEM columns change hands ----
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
     }
-    if (warp >= 4 && ((warp - 4) & 7) == 0 && lane == 0) tma_store_wait_all();
-    __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
