@@ -1,13 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- SpectralMixingLayer fwd+bwd tokens/s on B200 (BASELINE.json metric), one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f32|bf16] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f32|bf16] [--impl ours|reference] [--config cfg1|cfg2|cfg3|cfg5]
   N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
               bench.py --gpus N --steps K --warmup W
 
 A "step" is one forward + one backward of the layer over one batch of synthetic input.  Workload at N=1 is
 BASELINE.json configs[1]: SpectralMixingLayer(embed_dim=768), x = (16, 8192, 768); weak scaling (each rank holds its
 own batch of 16, i.e. the batch axis is sharded) with one NCCL all-reduce(sum) of the filter/bias gradients per step.
+
+--config selects another BASELINE.json configuration (default cfg2 = configs[1], the one the metric is quoted on):
+  cfg1  configs[0]  (8, 512, 256) fp32                       correctness-sized, launch bound
+  cfg3  configs[2]  (64, 4096, 1024) fp32, STRONG scaling: the batch of 64 is split over the N ranks, filter-gradient all-reduce
+  cfg5  configs[4]  long-context sweep T = 1K .. 128K at embed 1024, 2^20 tokens per step split over the N ranks by batch; one line
+        with a `sweep` list (per T: tokens/s, HBM-roofline fraction, and at N=1 the CPU arm on a batch-1 sample)
 
 One JSON line on stdout (rank 0):
   value        whole-job tokens/s (tokens = B*T summed over ranks), inputs resident in HBM, CUDA-event timed
@@ -90,51 +96,107 @@ def parse():
     ap.add_argument("--embed", type=int, default=CFG["D"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-batch", type=int, default=2)
-    return ap.parse_args()
+    ap.add_argument("--cpu-sample-batch", type=int, default=0, help="CPU legs: batch of the timed sample (0 = reference arm: the full batch; cpu_baseline leg: 2)")
+    ap.add_argument("--config", choices=["cfg1", "cfg2", "cfg3", "cfg5"], default="cfg2")
+    ap.add_argument("--no-bf16", action="store_true", help="skip the bf16 I/O sub-record of the default line")
+    args = ap.parse_args()
+    args.scaling = "weak"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config == "cfg1":
+        args.batch, args.seq, args.embed = 8, 512, 256
+    elif args.config == "cfg3":      # strong scaling: global batch 64 split over the ranks
+        args.batch, args.seq, args.embed, args.scaling = max(1, 64 // world), 4096, 1024, "strong"
+    return args
+
+
+def workload_config(args, world):
+    """The `config` object, identical for both arms (the driver compares them)."""
+    B, T, D = args.batch, args.seq, args.embed
+    k = min(D // 2, T // 2)
+    return {"workload": f"SpectralMixingLayer(embed_dim={D}) fwd+bwd, x=({B},{T},{D}) per GPU, {args.dtype} I/O, fp32 math, "
+                        f"k={k} live bins, randn x/g/filter, dropout 0 (BASELINE.json {args.config})",
+            "io_dtype": args.dtype, "global_batch": world * B, "seq_len": T, "embed_dim": D,
+            "parallelism": f"batch-sharded x{world}"}
 
 
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's torch port (== the reference's torch.fft algorithm) on the host cores
 # ------------------------------------------------------------------------------------------------------------
+def load_reference_module():
+    """The UNMODIFIED fft_tensor/spectral_layers.py from baseline/_ref (placed there by __graft_entry__.build() where the
+    reference is mounted; git-ignored, travels with gpurun), imported by file path (the package __init__ prints a banner
+    and sets a global memory limit).  None if it is not there."""
+    import importlib.util
+    path = os.path.join(ROOT, "baseline", "_ref", "fft_tensor", "spectral_layers.py")
+    if not os.path.exists(path):
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location("ref_spectral_layers", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    except Exception:
+        return None
+
+
 def cpu_reference_step_time(B, T, D, steps, warmup, budget_s=None):
-    from oracle import spectral_mixing_oracle as orc   # allowed here: cpu_baseline / --impl reference legs only
+    """Seconds per fwd+bwd step of the reference on the host cores.  Returns (dt, steps timed, threads, kind, what)."""
     torch.set_num_threads(os.cpu_count() or 1)
     gen = torch.Generator().manual_seed(0)
     Fn = D // 2
     w_re, w_im, bias = torch.randn(D, Fn, generator=gen), torch.randn(D, Fn, generator=gen), torch.randn(D, generator=gen)
     x, g = torch.randn(B, T, D, generator=gen), torch.randn(B, T, D, generator=gen)
+    ref = load_reference_module()
+    if ref is not None:
+        layer = ref.SpectralMixingLayer(D)
+        with torch.no_grad():
+            layer.weight_real.copy_(w_re); layer.weight_imag.copy_(w_im); layer.bias.copy_(bias)
+        kind, what = "reference", "unmodified fft_tensor/spectral_layers.py (baseline/_ref)"
+
+        def step():
+            layer.zero_grad(set_to_none=True)
+            xr = x.detach().requires_grad_(True)
+            layer(xr).backward(g)
+    else:
+        from oracle import spectral_mixing_oracle as orc   # allowed here: cpu_baseline / --impl reference legs only
+        kind, what = "port", "oracle torch port of spectral_layers.py:83-118"
+
+        def step():
+            orc.torch_port_fwd_bwd(x, w_re, w_im, bias, g)
     for _ in range(warmup):
-        orc.torch_port_fwd_bwd(x, w_re, w_im, bias, g)
+        step()
     times = []
     t_start = time.perf_counter()
     for _ in range(steps):
         t0 = time.perf_counter()
-        orc.torch_port_fwd_bwd(x, w_re, w_im, bias, g)
+        step()
         times.append(time.perf_counter() - t0)
         if budget_s is not None and time.perf_counter() - t_start > budget_s and len(times) >= 3:
             break
-    return sum(times) / len(times), len(times), torch.get_num_threads()
+    return sum(times) / len(times), len(times), torch.get_num_threads(), kind, what
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    B = min(args.cpu_sample_batch, args.batch)
+    # the SAME configuration as the GPU arm: the full per-GPU batch, --steps and --warmup as given (a step of cfg-2 costs about
+    # 0.8 s on a 16-core host).  --cpu-sample-batch < batch keeps a smaller sample for smoke tests; a 240 s budget bounds a
+    # run that was started with a huge --steps (the line reports the steps actually timed).
+    B = args.batch if args.cpu_sample_batch <= 0 else min(args.cpu_sample_batch, args.batch)
     T, D = args.seq, args.embed
-    # at most --steps steps, and at most ~90 s of CPU work (the line reports the steps actually timed)
-    dt, n, threads = cpu_reference_step_time(B, T, D, args.steps, max(1, min(args.warmup, 2)), budget_s=90.0)
+    dt, n, threads, kind, what = cpu_reference_step_time(B, T, D, args.steps, args.warmup, budget_s=240.0)
     val = B * T / dt
+    cfg = workload_config(args, world)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"SpectralMixingLayer(embed_dim={D}) fwd+bwd, x=({args.batch},{T},{D}) fp32, k={min(D // 2, T // 2)}",
-                   "note": f"CPU arm: each step is a bounded sample of the workload, batch {B} of {args.batch} (columns are independent)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"oracle torch port (torch.fft, {_fft_backend()}, {_cpu_model()}), "
-                                   f"x=({B},{T},{D}) fwd+bwd, mean of {n} steps"},
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{what} (torch.fft, {_fft_backend()}, {_cpu_model()}), x=({B},{T},{D}) fp32 fwd+bwd"
+                                   + ("" if B == args.batch else f" (batch {B} of {args.batch}; columns are independent)")
+                                   + f", mean of {n} steps"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print_line(json.dumps(line))
@@ -223,9 +285,112 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
+class Problem:
+    """One (B, T, D, dtype) problem resident on the GPU: the module, its inputs, and timers for the step and the two C-ABI calls."""
+
+    def __init__(self, B, T, D, dtype_name, dev, rank, world):
+        from tensor_cuda_fft_b200 import SpectralMixingLayer, _native
+        self.B, self.T, self.D, self.dtype_name, self.dev, self.world = B, T, D, dtype_name, dev, world
+        self.Fn = D // 2
+        self.k = min(self.Fn, T // 2)
+        self.dtype = torch.float32 if dtype_name == "f32" else torch.bfloat16
+        self.esz = 4 if dtype_name == "f32" else 2
+        self.io = _native.DTYPE_F32 if dtype_name == "f32" else _native.DTYPE_BF16
+        self.native = _native
+        self.lib = _native.lib()
+        self.plan = _native.plan(B, T, D, self.Fn, self.io)
+        torch.manual_seed(0 + rank)
+        self.layer = SpectralMixingLayer(D).to(dev)
+        with torch.no_grad():
+            self.layer.weight_real.normal_()
+            self.layer.weight_imag.normal_()
+            self.layer.bias.normal_()
+        self.x = torch.randn(B, T, D, device=dev).to(self.dtype)
+        self.g = torch.randn(B, T, D, device=dev).to(self.dtype)
+
+    def step(self):
+        """forward + backward through the module API (autograd included); at N > 1 one flat all-reduce of the filter gradients."""
+        from tensor_cuda_fft_b200 import allreduce_filter_grads
+        self.layer.zero_grad(set_to_none=True)
+        xr = self.x.detach().requires_grad_(True)
+        y = self.layer(xr)
+        y.backward(self.g)
+        if self.world > 1:
+            allreduce_filter_grads([self.layer])
+        gx = xr.grad
+        xr.grad = None
+        return y, gx
+
+    def abi_calls(self):
+        """(fwd, bwd) closures over the raw C ABI on the current stream (per-kernel timing for the roofline)."""
+        lib, native = self.lib, self.native
+        B, T, D, Fn, io = self.B, self.T, self.D, self.Fn, self.io
+        stream = torch.cuda.current_stream().cuda_stream
+        wr, wi, bs = self.layer.weight_real.detach(), self.layer.weight_imag.detach(), self.layer.bias.detach()
+        y, gx = torch.empty_like(self.x), torch.empty_like(self.x)
+        xlow = torch.empty(max(lib.sml_xlow_bytes(B, T, D, Fn), 8), dtype=torch.uint8, device=self.dev)
+        gflat = torch.empty(2 * D * Fn + D, device=self.dev)     # [gw_re | gw_im | gb], the host module's layout
+        gwr, gwi, gb = gflat[:D * Fn], gflat[D * Fn:2 * D * Fn], gflat[2 * D * Fn:]
+        ws_bytes = lib.sml_workspace_bytes(B, T, D, Fn, io)
+        ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=self.dev)
+        x, g = self.x, self.g
+        self._keep = (y, gx, xlow, gflat, ws)
+
+        def fwd():
+            native.check(lib.sml_forward(x.data_ptr(), wr.data_ptr(), wi.data_ptr(), bs.data_ptr(), y.data_ptr(),
+                                         xlow.data_ptr(), B, T, D, Fn, io, stream))
+
+        def bwd():
+            native.check(lib.sml_backward(g.data_ptr(), xlow.data_ptr(), wr.data_ptr(), wi.data_ptr(), gx.data_ptr(),
+                                          gwr.data_ptr(), gwi.data_ptr(), gb.data_ptr(), ws.data_ptr(), ws_bytes,
+                                          B, T, D, Fn, io, stream))
+        return fwd, bwd
+
+    # byte counts (SURVEY.md section 8d): the ALGORITHMIC floor does not count what the implementation adds (X_low, partial sums)
+    def bytes_step(self):
+        return 4 * self.B * self.T * self.D * self.esz
+
+    def bytes_fwd(self):
+        return 2 * self.B * self.T * self.D * self.esz + (2 * self.D * self.Fn + self.D) * 4
+
+    def bytes_bwd(self):
+        return 2 * self.B * self.T * self.D * self.esz + 2 * (2 * self.D * self.Fn + self.D) * 4
+
+    def bytes_impl_extra(self):
+        xl = self.B * self.D * self.k * 8
+        return {"fwd_xlow_write": xl, "bwd_xlow_read": xl, "bwd_partial_terms_write_read": 2 * xl}
+
+
+def time_steps(fn, steps, warmup, barrier):
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def time_kernel(fn, n):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) for a, b in evs]
+    return sum(ts) / len(ts), min(ts)
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from tensor_cuda_fft_b200 import SpectralMixingLayer, _native, allreduce_filter_grads
+    from tensor_cuda_fft_b200 import _native
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -236,44 +401,36 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = _native.lib()
-
-    B, T, D = args.batch, args.seq, args.embed
-    Fn = D // 2
-    k = min(Fn, T // 2)
-    dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
-    esz = 4 if args.dtype == "f32" else 2
-    io = _native.DTYPE_F32 if args.dtype == "f32" else _native.DTYPE_BF16
-    plan = _native.plan(B, T, D, Fn, io)
-
-    torch.manual_seed(0 + rank)
-    layer = SpectralMixingLayer(D).to(dev)
-    with torch.no_grad():
-        layer.weight_real.normal_()
-        layer.weight_imag.normal_()
-        layer.bias.normal_()
-    x = torch.randn(B, T, D, device=dev).to(dtype)
-    g = torch.randn(B, T, D, device=dev).to(dtype)
-
-    def step():
-        layer.zero_grad(set_to_none=True)
-        xr = x.detach().requires_grad_(True)
-        y = layer(xr)
-        y.backward(g)
-        if world > 1:
-            allreduce_filter_grads([layer])     # one flat NCCL all-reduce(sum) of [gw_re | gw_im | gb]
-        gx = xr.grad
-        xr.grad = None
-        return y, gx
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
+    peak, peak_src = load_peaks()
+
+    def roof(nbytes, ms):
+        ach = nbytes / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
+
+    if args.config == "cfg5":
+        run_sweep(args, dev, rank, world, barrier, max_over_ranks, roof)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    B, T, D = args.batch, args.seq, args.embed
+    prob = Problem(B, T, D, args.dtype, dev, rank, world)
     sampler = ClockSampler(local)      # separate process; started before the warm-up so it is sampling by the time we measure
     for _ in range(max(args.warmup, 3)):
-        step()
+        prob.step()
     barrier()
 
     # ---- timed region: exactly K steps, CUDA events, max over ranks ----
@@ -283,22 +440,17 @@ def run_ours(args):
     sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
-        step()
+        prob.step()
     e1.record()
     barrier()
     sampler.mark_end()
     launches = _native.launch_count() - n0
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = t.item()
-    ms_step = ms_total / args.steps
-    if ms_total < 100.0:
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    if ms_step * args.steps < 100.0:
         # the timed region is shorter than a few sampling periods: keep the same load running (untimed, the same number of
         # extra steps on every rank) until the sampler has seen ~0.2 s of it, and say so in the clocks record
         for _ in range(min(5000, int(200.0 / ms_step) + 1)):
-            step()
+            prob.step()
         barrier()
         sampler.t1 = time.time()
         sampler.note = "timed region < 0.1 s: window extended over an untimed continuation of the same steps"
@@ -306,115 +458,61 @@ def run_ours(args):
     value = world * B * T / (ms_step * 1e-3)
 
     # ---- per-kernel timing through the raw C ABI (events on the launching stream), for the roofline ----
-    stream = torch.cuda.current_stream().cuda_stream
-    wr, wi, bs = layer.weight_real.detach(), layer.weight_imag.detach(), layer.bias.detach()
-    y = torch.empty_like(x)
-    gx = torch.empty_like(x)
-    xlow = torch.empty(max(lib.sml_xlow_bytes(B, T, D, Fn), 8), dtype=torch.uint8, device=dev)
-    gflat = torch.empty(2 * D * Fn + D, device=dev)     # [gw_re | gw_im | gb], the host module's layout
-    gwr, gwi, gb = gflat[:D * Fn].view(D, Fn), gflat[D * Fn:2 * D * Fn].view(D, Fn), gflat[2 * D * Fn:]
-    ws_bytes = lib.sml_workspace_bytes(B, T, D, Fn, io)
-    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
-
-    def fwd():
-        _native.check(lib.sml_forward(x.data_ptr(), wr.data_ptr(), wi.data_ptr(), bs.data_ptr(), y.data_ptr(),
-                                      xlow.data_ptr(), B, T, D, Fn, io, stream))
-
-    def bwd():
-        _native.check(lib.sml_backward(g.data_ptr(), xlow.data_ptr(), wr.data_ptr(), wi.data_ptr(), gx.data_ptr(),
-                                       gwr.data_ptr(), gwi.data_ptr(), gb.data_ptr(), ws.data_ptr(), ws_bytes,
-                                       B, T, D, Fn, io, stream))
-
-    def time_kernel(fn, n):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
-        for a, b in evs:
-            a.record()
-            fn()
-            b.record()
-        torch.cuda.synchronize()
-        ts = [a.elapsed_time(b) for a, b in evs]
-        return sum(ts) / len(ts), min(ts)
-
+    fwd, bwd = prob.abi_calls()
     nk = min(max(args.steps, 10), 100)
     fwd_ms, fwd_min = time_kernel(fwd, nk)
     bwd_ms, bwd_min = time_kernel(bwd, nk)
-    peak, peak_src = load_peaks()
-    xlow_bytes = B * D * k * 8
-    param_bytes = (2 * D * Fn + D) * 4
-    bytes_fwd = 2 * B * T * D * esz + xlow_bytes + param_bytes
-    bytes_bwd = 2 * B * T * D * esz + xlow_bytes + 2 * param_bytes
-    bytes_step = 4 * B * T * D * esz     # the 4-pass floor (read x, write y, read g, write gx)
-
-    def roof(nbytes, ms):
-        ach = nbytes / (ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
-
     traffic = {}
-    try:    # measured DRAM bytes per launch from the committed ncu capture (only for the exact profiled configuration)
+    try:    # DRAM bytes per launch QUOTED from the committed ncu capture of exactly this configuration (not measured in this run)
         if (B, T, D, args.dtype) == (16, 8192, 768, "f32"):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["cfg2_f32"]
     except Exception:
         traffic = {}
-    roofline = roof(bytes_bwd, bwd_ms)
-    roofline.update({"kernel": "sml_backward = sml_fast_kernel<BWD> (fused analysis + Wirtinger filter-grad terms + synthesis) + filtergrad_reduce_kernel" if plan["path"] == "fast" else "generic kernels",
-                     "launch_ms": bwd_ms, "launch_ms_min": bwd_min, "algorithmic_bytes": bytes_bwd, "peak_source": peak_src,
-                     "traffic": traffic.get("sml_backward"), "traffic_source": "profiles/traffic.json (ncu --set full)" if traffic else None})
-    roofline_fwd = roof(bytes_fwd, fwd_ms)
-    roofline_fwd.update({"kernel": "sml_fast_kernel<FWD>", "launch_ms": fwd_ms, "launch_ms_min": fwd_min, "algorithmic_bytes": bytes_fwd,
-                         "traffic": traffic.get("sml_forward")})
-    roofline_step = roof(bytes_step, ms_step)
-    roofline_step.update({"note": "4-pass floor bytes / whole fwd+bwd step time (includes host launch gaps and, at N>1, the all-reduce)"})
+    fast = prob.plan["path"] == "fast"
+    roofline = roof(prob.bytes_bwd(), bwd_ms)
+    roofline.update({"kernel": "sml_backward = fused analysis + Wirtinger filter-gradient terms + synthesis kernel, + filtergrad_reduce_kernel" if fast else "generic kernels",
+                     "launch_ms": bwd_ms, "launch_ms_min": bwd_min, "algorithmic_bytes": prob.bytes_bwd(), "peak_source": peak_src,
+                     "algorithmic_bytes_note": "SURVEY.md 8(d): read g + write gx + filter read + gradients written; X_low and the per-batch partial terms are implementation traffic (implementation_extra_bytes), not counted",
+                     "implementation_extra_bytes": prob.bytes_impl_extra(),
+                     "traffic": traffic.get("sml_backward"),
+                     "traffic_source": "QUOTED from profiles/traffic.json (ncu --set full capture of this configuration, round 1), not measured in this run" if traffic else None})
+    roofline_fwd = roof(prob.bytes_fwd(), fwd_ms)
+    roofline_fwd.update({"kernel": "sml_forward (one fused kernel)", "launch_ms": fwd_ms, "launch_ms_min": fwd_min,
+                         "algorithmic_bytes": prob.bytes_fwd(), "traffic": traffic.get("sml_forward")})
+    roofline_step = roof(prob.bytes_step(), ms_step)
+    roofline_step.update({"note": "4-pass floor bytes / whole fwd+bwd step time (includes launch gaps and, at N>1, the all-reduce)"})
+
+    # ---- bf16 I/O of the same configuration (BASELINE.json configs[1] names both): a sub-record of the default line ----
+    bf16 = None
+    if args.dtype == "f32" and args.config == "cfg2" and not args.no_bf16:
+        try:
+            pb = Problem(B, T, D, "bf16", dev, rank, world)
+            ms_b = max_over_ranks(time_steps(pb.step, min(args.steps, 100), 5, barrier))
+            fb, bb = pb.abi_calls()
+            fb_ms, _ = time_kernel(fb, 30)
+            bb_ms, _ = time_kernel(bb, 30)
+            bf16 = {"value": world * B * T / (ms_b * 1e-3), "unit": UNIT, "ms_per_step": ms_b, "io_dtype": "bf16",
+                    "kernels": "tensor-core (tcgen05) kernels, csrc/sml_tc.cuh" if os.environ.get("SML_TC", "") == "1" or _tc_default() else "CUDA-core butterfly kernels, csrc/sml_fast.cuh",
+                    "roofline_step": roof(pb.bytes_step(), ms_b), "roofline_fwd": dict(roof(pb.bytes_fwd(), fb_ms), launch_ms=fb_ms),
+                    "roofline_bwd": dict(roof(pb.bytes_bwd(), bb_ms), launch_ms=bb_ms)}
+            del pb, fb, bb
+            torch.cuda.empty_cache()
+        except Exception as e:   # the sub-record must never cost the headline line
+            bf16 = {"unavailable": str(e).splitlines()[0][:200]}
 
     # ---- end to end: the reference-facing C-ABI call with HOST buffers (sml_fwd_bwd_host): pinned host x, g in;
     #      y, gx and the filter/bias gradients back in host memory; all copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        from tensor_cuda_fft_b200 import spectral_mix_fwd_bwd_host
-        xh = torch.empty(B, T, D, dtype=dtype).pin_memory()
-        gh = torch.empty(B, T, D, dtype=dtype).pin_memory()
-        xh.copy_(x.detach())
-        gh.copy_(g.detach())
-        yh = torch.empty(B, T, D, dtype=dtype).pin_memory()
-        gxh = torch.empty(B, T, D, dtype=dtype).pin_memory()
-        wr_h, wi_h, bs_h = wr.cpu(), wi.cpu(), bs.cpu()
-        torch.cuda.synchronize()
+        e2e = run_e2e(prob, args, world, dev, barrier, max_over_ranks)
 
-        def e2e_step():
-            _, _, gwr_h, gwi_h, gb_h = spectral_mix_fwd_bwd_host(xh, gh, wr_h, wi_h, bs_h, out=(yh, gxh), device=dev)
-            if world > 1:   # filter-gradient sum across ranks (tiny: staged through the device for NCCL)
-                flat = torch.cat([gwr_h.reshape(-1), gwi_h.reshape(-1), gb_h]).to(dev)
-                dist.all_reduce(flat)
-                flat.cpu()
-
-        n_e2e = max(3, min(args.steps, 10))
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()      # the call is synchronous (host buffers complete on return): wall clock is exact
-        for _ in range(n_e2e):
-            e2e_step()
-        torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        ms /= n_e2e
-        e2e = {"value": world * B * T / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * T * D * esz + param_bytes,
-               "d2h_bytes_per_step": 2 * B * T * D * esz + param_bytes, "ms_per_step": ms, "steps": n_e2e,
-               "api": "sml_fwd_bwd_host (C ABI, host pointers): pinned host x,g,params in; y, gx, filter/bias grads out; "
-                      "batch-chunked H2D / kernels / D2H pipeline on three streams"}
-
-    # ---- CPU baseline (rank 0, N=1 only) ----
+    # ---- CPU baseline (rank 0, N=1 only): a bounded sample of the same workload ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        Bs = min(args.cpu_sample_batch, B)
-        dt, n, threads = cpu_reference_step_time(Bs, T, D, steps=40, warmup=1, budget_s=12.0)
-        cpu = {"value": Bs * T / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"oracle torch port (torch.fft on host, {_fft_backend()}, {_cpu_model()}), "
+        Bs = min(args.cpu_sample_batch if args.cpu_sample_batch > 0 else 2, B)
+        dt, n, threads, kind, what = cpu_reference_step_time(Bs, T, D, steps=40, warmup=1, budget_s=12.0)
+        cpu = {"value": Bs * T / dt, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{what} (torch.fft on host, {_fft_backend()}, {_cpu_model()}), "
                          f"x=({Bs},{T},{D}) fp32 fwd+bwd (batch {Bs} of {B}; columns independent), mean of {n} steps",
                "ms_per_step": dt * 1e3}
 
@@ -422,30 +520,113 @@ def run_ours(args):
     gpu_ref = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            ms_ref = gpu_reference_algorithm(x, g, wr, wi, bs)
+            wr, wi, bs = prob.layer.weight_real.detach(), prob.layer.weight_imag.detach(), prob.layer.bias.detach()
+            ms_ref = gpu_reference_algorithm(prob.x, prob.g, wr, wi, bs)
             gpu_ref = {"value": B * T / (ms_ref * 1e-3), "unit": UNIT, "ms_per_step": ms_ref,
                        "what": "reference algorithm (torch.fft/cuFFT + ATen elementwise + autograd, fp32) on the same B200 and shape; context, not an arm"}
         except Exception as e:   # e.g. out of memory at very large shapes: context only
             gpu_ref = {"unavailable": str(e).splitlines()[0][:200]}
 
     if rank == 0:
+        esz = prob.esz
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",      # arithmetic type of the path (bf16 is an I/O type only)
-            "config": {"io_dtype": args.dtype, "workload": f"SpectralMixingLayer(embed_dim={D}) fwd+bwd, x=({B},{T},{D}) per GPU, {args.dtype} I/O, fp32 math, "
-                                   f"k={k} live bins, randn x/g/filter, dropout 0 (BASELINE.json configs[1])",
-                       "global_batch": world * B, "seq_len": T, "embed_dim": D, "parallelism": f"batch-sharded x{world}",
-                       "plan": plan, "l2": f"inputs larger than L2 ({2 * B * T * D * esz / 1e6:.0f} MB read per step vs 126 MB), no flush",
-                       "collective": "none" if world == 1 else f"1 all-reduce(sum) of [gw_re|gw_im|gb] per step ({_collective_path()})"},
+            "config": workload_config(args, world),
+            "impl_detail": {"plan": prob.plan, "l2": f"inputs larger than L2 ({2 * B * T * D * esz / 1e6:.0f} MB read per step vs 126 MB), no flush"
+                                                    if 2 * B * T * D * esz > 126e6 else "inputs smaller than L2, no flush: launch-bound configuration",
+                            "collective": "none" if world == 1 else f"1 all-reduce(sum) of [gw_re|gw_im|gb] per step ({_collective_path()})"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_step": roofline_step,
+            "bf16": bf16,
             "e2e": e2e, "cpu_baseline": cpu, "reference_algorithm_on_gpu": gpu_ref,
         }
         print_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _tc_default():
+    try:
+        from tensor_cuda_fft_b200 import _native
+        return bool(getattr(_native, "TC_DEFAULT", False))
+    except Exception:
+        return False
+
+
+def run_e2e(prob, args, world, dev, barrier, max_over_ranks):
+    import torch.distributed as dist
+    from tensor_cuda_fft_b200 import spectral_mix_fwd_bwd_host
+    B, T, D, dtype, esz = prob.B, prob.T, prob.D, prob.dtype, prob.esz
+    param_bytes = (2 * D * prob.Fn + D) * 4
+    xh = torch.empty(B, T, D, dtype=dtype).pin_memory()
+    gh = torch.empty(B, T, D, dtype=dtype).pin_memory()
+    xh.copy_(prob.x.detach())
+    gh.copy_(prob.g.detach())
+    yh = torch.empty(B, T, D, dtype=dtype).pin_memory()
+    gxh = torch.empty(B, T, D, dtype=dtype).pin_memory()
+    wr_h, wi_h, bs_h = prob.layer.weight_real.detach().cpu(), prob.layer.weight_imag.detach().cpu(), prob.layer.bias.detach().cpu()
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        _, _, gwr_h, gwi_h, gb_h = spectral_mix_fwd_bwd_host(xh, gh, wr_h, wi_h, bs_h, out=(yh, gxh), device=dev)
+        if world > 1:   # filter-gradient sum across ranks (tiny: staged through the device for NCCL)
+            flat = torch.cat([gwr_h.reshape(-1), gwi_h.reshape(-1), gb_h]).to(dev)
+            dist.all_reduce(flat)
+            flat.cpu()
+
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()      # the call is synchronous (host buffers complete on return): wall clock is exact
+    for _ in range(n_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_e2e
+    return {"value": world * B * T / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * T * D * esz + param_bytes,
+            "d2h_bytes_per_step": 2 * B * T * D * esz + param_bytes, "ms_per_step": ms, "steps": n_e2e,
+            "api": "sml_fwd_bwd_host (C ABI, host pointers): pinned host x,g,params in; y, gx, filter/bias grads out; "
+                   "batch-chunked H2D / kernels / D2H pipeline on three streams"}
+
+
+def run_sweep(args, dev, rank, world, barrier, max_over_ranks, roof):
+    """BASELINE.json configs[4]: long-context sweep T = 1K .. 128K, embed 1024, 2^20 tokens per step split over the ranks by
+    batch, fp32 (or --dtype bf16); at N = 1 the CPU arm runs next to it on a batch-1 sample of every length."""
+    D = 1024
+    rows, tok_total, ms_total = [], 0, 0.0
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    first = True
+    for T in (1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072):
+        Bg = max(world, (1 << 20) // T)
+        B = max(1, Bg // world)
+        prob = Problem(B, T, D, args.dtype, dev, rank, world)
+        if first:
+            sampler.mark_begin()
+            first = False
+        ms = max_over_ranks(time_steps(prob.step, max(5, min(args.steps, 30)), max(args.warmup, 3), barrier))
+        row = {"seq_len": T, "batch_per_gpu": B, "ms_per_step": ms, "value": world * B * T / (ms * 1e-3), "unit": UNIT,
+               "roofline_step_frac": roof(prob.bytes_step(), ms)["frac"], "plan": prob.plan}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            dt, n, threads, kind, _ = cpu_reference_step_time(1, T, D, steps=3, warmup=1, budget_s=4.0)
+            row["cpu_reference"] = {"value": T / dt, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"x=(1,{T},{D}) fp32, {n} steps"}
+        rows.append(row)
+        tok_total += world * B * T
+        ms_total += ms
+        del prob
+        torch.cuda.empty_cache()
+    sampler.mark_end()
+    clocks = sampler.stop()
+    if rank == 0:
+        line = {"metric": METRIC, "value": tok_total / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": max(5, min(args.steps, 30)),
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / len(rows), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"long-context sweep T=1K..128K, embed 1024, 2^20 tokens per step, {args.dtype} I/O (BASELINE.json cfg5)",
+                           "io_dtype": args.dtype, "parallelism": f"batch-sharded x{world}"},
+                "value_note": "tokens of all eight lengths / sum of their step times", "clocks": clocks, "sweep": rows}
+        print_line(json.dumps(line))
 
 
 def main():

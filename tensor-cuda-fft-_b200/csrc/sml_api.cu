@@ -42,6 +42,7 @@ const Knobs& knobs() {
         if (const char* e = getenv("SML_FAST_CTAS")) v.fast_ctas = atoi(e);
         if (const char* e = getenv("SML_FAST_XB")) v.fast_xb = atoi(e);
         if (const char* e = getenv("SML_TC")) v.tc = atoi(e) != 0 ? 1 : 0;
+        if (const char* e = getenv("SML_PDL")) v.pdl = atoi(e) != 0 ? 1 : 0;
         return v;
     }();
     return k;
@@ -121,7 +122,7 @@ unsigned int* debug_record() {
         const char* e = getenv("SML_DEBUG");
         if (e == nullptr || atoi(e) == 0) return;
         if (cudaHostAlloc(&g_dbg_host, 8192, cudaHostAllocMapped) != cudaSuccess) { g_dbg_host = nullptr; return; }
-        memset(g_dbg_host, 0, 8192);
+        memset(g_dbg_host, 0, 8192);   // words 0..1023: mbarrier-timeout records; words 1024..: phase timeline of the tensor-core kernel
         if (cudaHostGetDevicePointer(&dev, g_dbg_host, 0) != cudaSuccess) dev = nullptr;
     });
     return dev;
@@ -306,10 +307,9 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
             if (sml_host::launch_tc<true>(g, gx, a, st->sm_count, stream)) return 1;
             if (want_grads) {
                 const long long n = (long long)D * ((F + 1) / 2);
-                sml::filtergrad_reduce_kernel<<<(unsigned)((n + 63) / 64), dim3(64, 4), 0, stream>>>(
-                    reinterpret_cast<const float2*>(gpart), gbpart, gw_re, gw_im, gb, B, D, F, p.k);
+                SML_CUDA(sml_host::launch_pdl(sml::filtergrad_reduce_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
+                                              reinterpret_cast<const float2*>(gpart), (const float*)gbpart, gw_re, gw_im, gb, B, D, F, p.k));
                 count_launch();
-                SML_CUDA(cudaGetLastError());
             }
             return 0;
         }
@@ -333,10 +333,9 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         if (launch_fast<IO, true>(p, map, map_out, prm, grid, stream)) return 1;
         if (want_grads) {
             const long long n = (long long)D * ((F + 1) / 2);
-            sml::filtergrad_reduce_kernel<<<(unsigned)((n + 63) / 64), dim3(64, 4), 0, stream>>>(
-                reinterpret_cast<const float2*>(prm.gpart), prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k);
+            SML_CUDA(sml_host::launch_pdl(sml::filtergrad_reduce_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
+                                          reinterpret_cast<const float2*>(prm.gpart), (const float*)prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k));
             count_launch();
-            SML_CUDA(cudaGetLastError());
         }
         return 0;
     }
@@ -582,6 +581,18 @@ int sml_debug_dump(void) {
     if (g_dbg_host == nullptr) return 0;
     const unsigned int n = g_dbg_host[0];
     fprintf(stderr, "sml_debug: %u timed-out mbarrier waits recorded\n", n);
+    {   // phase timeline of the last tensor-core launch (CTA 0): start, analysis done, mid done, synthesis done -- per work item
+        const unsigned long long* tl = reinterpret_cast<const unsigned long long*>(g_dbg_host + 1024);
+        for (int it = 0; it < 8 && tl[4 * it] != 0; ++it)
+            fprintf(stderr, "  tc timeline item %d: analysis %.2f us, mid %.2f us, synthesis %.2f us%s\n", it, (tl[4 * it + 1] - tl[4 * it]) * 1e-3,
+                    (tl[4 * it + 2] - tl[4 * it + 1]) * 1e-3, (tl[4 * it + 3] - tl[4 * it + 2]) * 1e-3,
+                    it > 0 ? "" : "  (first item: includes the cold start)");
+        const unsigned long long* ta = reinterpret_cast<const unsigned long long*>(g_dbg_host + 1024 + 64);
+        for (int it = 0; it < 8 && tl[4 * it] != 0; ++it)
+            fprintf(stderr, "  tc timeline item %d, warp 4 (us): E1 wait-x %.2f wait-mma %.2f work %.2f | EA wait %.2f work %.2f | EB wait %.2f work %.2f | mid+other %.2f\n",
+                    it, ta[8 * it] * 1e-3, ta[8 * it + 1] * 1e-3, ta[8 * it + 2] * 1e-3, ta[8 * it + 3] * 1e-3, ta[8 * it + 4] * 1e-3,
+                    ta[8 * it + 5] * 1e-3, ta[8 * it + 6] * 1e-3, ta[8 * it + 7] * 1e-3);
+    }
     for (unsigned int t = 0; t < 31u; ++t) {
         const unsigned int cnt = g_dbg_host[1 + t];
         if (cnt == 0) continue;

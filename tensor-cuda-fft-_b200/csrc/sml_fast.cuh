@@ -136,6 +136,10 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 // wait until the bulk stores issued by this thread have finished READING shared memory
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// programmatic dependent launch: wait for the predecessor grid in the stream (all of its memory operations are visible
+// afterwards); let the successor grid start its own prologue
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // make generic-proxy shared-memory writes visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -433,6 +437,10 @@ __global__ void __launch_bounds__(NR* P, MINB)
         xdone[1] = 0u;
     }
     __syncthreads();
+    // everything above ran concurrently with the tail of the previous kernel in the stream (PDL); from here on this
+    // kernel reads what that kernel may have written (x / g, X_low) and overwrites what it may still be reading
+    griddep_wait();
+    griddep_launch_dependents();
     if (tid == 0) {
         issue_load(0);
         if constexpr (XB == 2) issue_load(1);
@@ -575,6 +583,8 @@ static __global__ void __launch_bounds__(256) filtergrad_reduce_kernel(const flo
     // block (64, 4): threadIdx.x -> pair of bins, threadIdx.y -> every 4th batch element; the four partial sums are combined
     // through shared memory in a fixed order (b-slices 0, 1, 2, 3), so the result does not depend on scheduling
     __shared__ float4 part[3][64];
+    griddep_wait();                // the fused backward kernel wrote gpart / gbpart (PDL: this grid may be resident before it ends)
+    griddep_launch_dependents();
     const int F2 = (F + 1) / 2;
     const long long idx = (long long)blockIdx.x * 64 + threadIdx.x;
     const bool valid = idx < (long long)D * F2;

@@ -24,6 +24,7 @@ struct Knobs {
     int fast_ctas = 0;   // 2 or 3: CTAs per SM of the NR = 32, KJ = 12 kernel (0 = default)
     int fast_xb = 0;     // 1 or 2: TMA landing tiles (0 = default)
     int tc = -1;         // 0 / 1: tensor-core kernel for eligible bf16 problems (-1 = default)
+    int pdl = 0;         // SML_PDL=1: launch with programmatic dependent launch (measured slower inside the fwd/bwd/reduce chain: off by default)
 };
 const Knobs& knobs();
 
@@ -32,6 +33,24 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency)
 int get_encode_fn(EncodeTiledFn* out);
+
+// Launch with programmatic stream serialization (PDL): the kernel may become resident and run its prologue (barrier setup,
+// table staging) while its predecessor in the stream drains; every kernel of this library executes griddepcontrol.wait
+// before it touches global data another kernel may have written, and triggers its own dependents right after that.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = knobs().pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- tensor-core path (sml_inst_tc.cu) ----
 struct TcLaunch {

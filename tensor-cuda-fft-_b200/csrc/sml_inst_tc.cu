@@ -148,9 +148,9 @@ bool tc_eligible(int T, int D, int k, int io_dtype) {
     return io_dtype == SML_DTYPE_BF16 && D % 32 == 0 && T % 512 == 0 && T >= 512 && T <= 16384 && k >= 1 && k <= 512 && k <= T / 2;
 }
 
-template <bool BWD, bool DUMP>
+template <bool BWD, int MODE>
 int launch_tc_inst(const CUtensorMap& map_in, const sml::TcParams& prm, int grid, size_t smem_bytes, cudaStream_t stream) {
-    auto kern = sml::sml_tc_kernel<BWD, DUMP>;
+    auto kern = sml::sml_tc_kernel<BWD, MODE>;
     static std::atomic<unsigned long long> attr_done{0};   // per kernel instantiation: one bit per device ordinal
     int dev = 0;
     SML_CUDA(cudaGetDevice(&dev));
@@ -159,9 +159,8 @@ int launch_tc_inst(const CUtensorMap& map_in, const sml::TcParams& prm, int grid
         SML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done.fetch_or(bit, std::memory_order_release);
     }
-    kern<<<grid, sml::tc::THREADS, smem_bytes, stream>>>(map_in, prm);
+    SML_CUDA(launch_pdl(kern, dim3(grid), dim3(sml::tc::THREADS), smem_bytes, stream, map_in, prm));
     count_launch();
-    SML_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -188,6 +187,8 @@ int launch_tc(const void* in, void* out, const TcLaunch& a, int sm_count, cudaSt
     if (nslot > sml::tc::MAX_SLOT) nslot = sml::tc::MAX_SLOT;
     if (nslot < 4) return fail("internal: tensor-core path without room for its x tiles (T=%d)", a.T);
     prm.nslot = nslot;
+    static const int cfence = [] { const char* e = getenv("SML_TC_CFENCE"); return e ? atoi(e) : 0; }();
+    prm.consumer_fence = cfence;
     const size_t smem_bytes = sml::tc::smem_map(prm.N2, nslot).total;
     const int grid = prm.nitems < sm_count ? prm.nitems : sm_count;
     // bring-up aid: SML_TC_DUMP=<file> writes the intermediates of work item 0 of a FORWARD launch (tools/tc_dump_check.py)
@@ -196,7 +197,7 @@ int launch_tc(const void* in, void* out, const TcLaunch& a, int sm_count, cudaSt
         const size_t dump_floats = (size_t)prm.N2 * 2048 * 2 + 2 * 36864;
         SML_CUDA(cudaMalloc(&prm.dump, dump_floats * sizeof(float)));
         SML_CUDA(cudaMemset(prm.dump, 0, dump_floats * sizeof(float)));
-        if (launch_tc_inst<BWD, true>(map_in, prm, grid, smem_bytes, stream)) return 1;
+        if (launch_tc_inst<BWD, 1>(map_in, prm, grid, smem_bytes, stream)) return 1;
         SML_CUDA(cudaStreamSynchronize(stream));
         std::vector<float> host(dump_floats);
         SML_CUDA(cudaMemcpy(host.data(), prm.dump, dump_floats * sizeof(float), cudaMemcpyDeviceToHost));
@@ -204,7 +205,8 @@ int launch_tc(const void* in, void* out, const TcLaunch& a, int sm_count, cudaSt
         cudaFree(prm.dump);
         return 0;
     }
-    return launch_tc_inst<BWD, false>(map_in, prm, grid, smem_bytes, stream);
+    if (!BWD && prm.dbg != nullptr) return launch_tc_inst<BWD, 2>(map_in, prm, grid, smem_bytes, stream);   // SML_DEBUG=1: phase timing of CTA 0
+    return launch_tc_inst<BWD, 0>(map_in, prm, grid, smem_bytes, stream);
 }
 
 template int launch_tc<false>(const void*, void*, const TcLaunch&, int, cudaStream_t);

@@ -39,9 +39,8 @@ int launch_fast_xb(const CUtensorMap& map_in, const CUtensorMap& map_out, const 
     auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD, XB>;
     static std::atomic<unsigned long long> attr_done{0};   // per kernel instantiation (this function template)
     if (int rc = ensure_smem_attr(kern, C::SMEM_BYTES, attr_done)) return rc;
-    kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(map_in, map_out, prm);
+    SML_CUDA(launch_pdl(kern, dim3(grid), dim3(C::NT), C::SMEM_BYTES, stream, map_in, map_out, prm));
     count_launch();
-    SML_CUDA(cudaGetLastError());
     return 0;
 }
 

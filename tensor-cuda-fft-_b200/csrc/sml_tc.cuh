@@ -52,6 +52,7 @@ struct TcParams {
     int N2;                // T / 64
     int ntd;               // channel tiles = D / 32
     int nitems;            // B * ntd
+    int consumer_fence;    // see the kernel
     int nslot;             // x-tile landing slots (4..8): as many as shared memory allows, the analysis phase is TMA-latency bound
     void* out;             // y (FWD) / gx (BWD): (B,T,D) bf16, written with plain global stores
     float invT;
@@ -252,16 +253,21 @@ __device__ __forceinline__ void mid_row(const uint32_t (&z)[32], uint32_t (&outw
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <bool BWD, bool DUMP>
+template <bool BWD, int MODE>   // MODE 0 = production, 1 = intermediate dump (bring-up), 2 = phase timing (SML_DEBUG)
 __global__ void __launch_bounds__(tc::THREADS, 1)
     sml_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams prm) {
     using namespace tc;
+    constexpr bool DUMP = MODE == 1;
+    constexpr bool TIMING = MODE == 2;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int N2 = prm.N2;
     const int nslot = prm.nslot;
     const SmemMap sm = smem_map(N2, nslot);
     Bars* const bars = reinterpret_cast<Bars*>(smem + sm.bar);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Where the generic-proxy writes of the compute warps (operand tiles in shared memory) are fenced against the tensor core's
+    // async-proxy reads: by every writer before it arrives (0), or once by the MMA thread after it has acquired the barrier (1).
+    const bool consumer_fence = prm.consumer_fence != 0;
     const int NT1 = N2 >> 2;   // stage-1 / stage-B tiles (4 n each) per work item: even
     const int NCH = N2 >> 3;   // stage-2 / stage-A chunks (8 n each)
     unsigned int* const dbg = prm.dbg;
@@ -302,6 +308,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // the setup above (barriers, TMEM, constant tables) overlapped the tail of the previous kernel in the stream (PDL)
+    griddep_wait();
+    griddep_launch_dependents();
     const uint32_t tmem = bars->tmem_base;
     const uint32_t sbase = smem_u32(smem);
 
@@ -336,10 +345,35 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
         xadvance(1);
     };
 
+    // SML_DEBUG=1: CTA 0 records %globaltimer at its phase boundaries (words 1024.. of the host-mapped debug record)
+    auto mark = [&](int it, int phase) {
+        if (TIMING && dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && it < 8) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            reinterpret_cast<volatile uint64_t*>(dbg + 1024)[it * 4 + phase] = now;
+        }
+    };
+    // finer accounting (same switch): time warp 4 spends waiting / working inside the epilogues, accumulated per work item
+    const bool timing = TIMING && dbg != nullptr && blockIdx.x == 0 && warp == 4;
+    uint64_t tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+    auto tick = [&](int slot) {   // adds the time since the previous tick to tacc[slot]
+        if (timing) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            tacc[slot] += now - tlast;
+            tlast = now;
+        }
+    };
     for (int it = 0; it < my_items; ++it) {
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
         const int b = item / prm.ntd, dt = item - b * prm.ntd;
         const int d0 = dt * 32;
+        mark(it, 0);
+        if (timing) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tacc[q] = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tlast));
+        }
         const uint32_t gi0 = (uint32_t)it * (uint32_t)NT1;   // global tile / chunk use counters (barrier phases)
         const uint32_t gc0 = (uint32_t)it * (uint32_t)NCH;
 
@@ -373,6 +407,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 auto stage2 = [&](int c) {
                     const uint32_t uc = gc0 + c, s2 = uc & 1u;
                     mbar_wait_tc(&bars->a2_full[s2], (uc >> 1) & 1u, dbg, 3u, uc);
+                    if (consumer_fence) fence_proxy_async();
                     tc_fence_after();
                     const uint64_t bd = smem_desc(sbase + OFF_B2 + (uint32_t)(c >> 2) * 4096u + (uint32_t)(c & 3) * 32u, 16, 1024, LAYOUT_SW128);
 #pragma unroll 1
@@ -383,8 +418,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                     mma_commit(&bars->a2_free[s2]);
                 };
                 // ---- analysis ----
+                int c2 = 0;   // next stage-2 chunk: issued as soon as both of its tiles have been transposed (polled before every tile)
                 for (int i = 0; i < NT1; ++i) {
                     const uint32_t u = gi0 + i, p = u & 1u;
+                    if (c2 < NCH && 2 * c2 + 1 < i) {
+                        const uint32_t uc = gc0 + c2;
+                        if (mbar_try_wait(&bars->a2_full[uc & 1u], (uc >> 1) & 1u)) { stage2(c2); ++c2; }
+                    }
                     mbar_wait_tc(&bars->x_full[xs], xph, dbg, 4u, u);
                     mbar_wait_tc(&bars->d1_free[p], ((u >> 1) & 1u) ^ 1u, dbg, 5u, u);
                     tc_fence_after();
@@ -398,9 +438,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                     mma_commit(&bars->x_free[xs]);
                     mma_commit(&bars->d1_full[p]);
                     xadvance(1);
-                    if ((i & 1) && i >= 3) stage2((i - 3) >> 1);
+                    // never fall more than one chunk behind: the epilogue of chunk c2 + 2 needs the operand buffer of chunk c2
+                    if ((i & 1) && i >= 3 && c2 <= ((i - 3) >> 1)) { stage2(c2); ++c2; }
                 }
-                stage2(NCH - 1);
+                for (; c2 < NCH; ++c2) stage2(c2);
                 mma_commit(&bars->d2_full);
                 // ---- synthesis ----
                 auto stageA = [&](int c) {
@@ -422,7 +463,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                     const uint32_t u = gi0 + i, p = u & 1u;
                     const int c = i >> 1;
                     const uint32_t uc = gc0 + c, s = uc & 1u;
-                    if ((i & 1) == 0) mbar_wait_tc(&bars->ab_full[s], (uc >> 1) & 1u, dbg, 7u, uc);
+                    if ((i & 1) == 0) {
+                        mbar_wait_tc(&bars->ab_full[s], (uc >> 1) & 1u, dbg, 7u, uc);
+                        if (consumer_fence) fence_proxy_async();
+                    }
                     mbar_wait_tc(&bars->db_free[p], ((u >> 1) & 1u) ^ 1u, dbg, 8u, u);
                     tc_fence_after();
 #pragma unroll
@@ -434,6 +478,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                     mma_commit(&bars->db_full[p]);
                 };
                 mbar_wait_tc(&bars->aband_full, (uint32_t)it & 1u, dbg, 9u, (uint32_t)it);
+                if (consumer_fence) fence_proxy_async();
                 tc_fence_after();
                 stageA(0);
                 if (NCH > 1) stageA(1);
@@ -450,6 +495,23 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
             }
         } else if (warp >= 4) {
             // =========================== compute warps ===========================
+            // the mid phase reads this item's filter rows (BWD: and its X_low rows) once, cold: pull them into L2 now, one 128-byte
+            // line per thread and step, while the analysis streams
+            {
+                const int ct = cw * 32 + lane;                      // 0..511
+                const int lines = (prm.k * 4 + 127) / 128;          // lines per filter row
+                for (int idx = ct; idx < 32 * lines; idx += 512) {
+                    const int dl = idx / lines, ln = idx - dl * lines;
+                    const size_t off = (size_t)(d0 + dl) * prm.F + (size_t)ln * 32;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.w_re + off));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.w_im + off));
+                    if (BWD && prm.gw_re != nullptr) {
+                        const float2* xl = reinterpret_cast<const float2*>(prm.xlow) + ((size_t)b * prm.D + d0 + dl) * (size_t)prm.k + (size_t)ln * 32;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(xl));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(xl + 16));
+                    }
+                }
+            }
             // ---- analysis epilogue: stage-1 accumulator -> twiddle -> A2 chunk (transposed) ----
             for (int i = tp; i < NT1; i += 2) {
                 const uint32_t u = gi0 + i, p = u & 1u;
@@ -464,7 +526,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                         twv[2 * j + 1] = make_float2(q4.z, q4.w);
                     }
                 }
+                tick(0);   // [0] E1: x tile + twiddles landed
                 mbar_wait_tc(&bars->d1_full[p], (u >> 1) & 1u, dbg, 12u, u);
+                tick(1);   // [1] E1: stage-1 MMA done
                 tc_fence_after();
                 uint32_t v[32];
                 tmem_ld32(tq + COL_D1 + 64u * p + 32u * h, v);
@@ -503,14 +567,18 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                         }
                     }
                 }
-                fence_proxy_async();
+                if (!consumer_fence) fence_proxy_async();
                 warp_arrive(&bars->a2_full[s2], lane);
+                tick(2);   // [2] E1: TMEM load, twiddle, stores, fence
             }
 
+            tick(7);
+            mark(it, 1);
             // ---- mid phase: band accumulator -> filter -> band operand of the synthesis ----
             mbar_wait_tc(&bars->d2_full, (uint32_t)it & 1u, dbg, 14u, (uint32_t)it);
             tc_fence_after();
-            for (int t = wg; t < NTILE; t += 4) {
+            for (int t = (wg + it) & 3; t < NTILE; t += 4) {
+                if (128 * t + 32 * quad >= ROWS) continue;   // rows >= ROWS stay zero (initial fill; nothing ever writes them)
                 const int r = 128 * t + 32 * quad + lane;
                 uint32_t z[32];
                 tmem_ld32(tq + COL_D2 + 32u * t, z);
@@ -542,8 +610,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                     *reinterpret_cast<uint4*>(ab + pl * PLANE) = make_uint4(outw[4 * pl], outw[4 * pl + 1], outw[4 * pl + 2], outw[4 * pl + 3]);
             }
             tc_fence_before();
-            fence_proxy_async();
+            if (!consumer_fence) fence_proxy_async();
             warp_arrive(&bars->aband_full, lane);
+            mark(it, 2);
+            tick(7);   // [7] everything between the per-tile epilogues (mid phase, waits for d2 / band)
 
             // ---- synthesis epilogues, software-pipelined by one chunk: EA(c) then EB(tiles of chunk c-1) ----
             auto epilogueA = [&](int c) {
@@ -552,8 +622,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 mbar_wait_tc(&bars->da_full[s], (uc >> 1) & 1u, dbg, 16u, uc);
                 tc_fence_after();
                 mbar_wait_tc(&bars->ab_free[s], ((uc >> 1) & 1u) ^ 1u, dbg, 17u, uc);
+                tick(3);   // [3] EA: waits (twiddles, stage-A MMA, operand buffer free)
                 const float2* const twc = reinterpret_cast<const float2*>(smem + sm.tws + s * 2048u);
-                for (int t = wg; t < NTILE; t += 4) {
+                // nine tiles over four warpgroups: the group that takes three rotates with the chunk, so that over the double-buffered
+                // chunks the load evens out (every warp waits on the same barriers: a fixed assignment makes one group the critical path)
+                for (int t = (wg + c) & 3; t < NTILE; t += 4) {
+                    if (128 * t + 32 * quad >= ROWS) continue;   // the last tile is half empty
                     const int r = 128 * t + 32 * quad + lane;
                     const int dl = r / RPD, p = r - dl * RPD;
                     uint32_t v[16];
@@ -585,9 +659,10 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                     }
                 }
                 tc_fence_before();
-                fence_proxy_async();
+                if (!consumer_fence) fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&bars->ab_full[s]); mbar_arrive(&bars->da_free[s]); mbar_arrive(&bars->tws_free[s]); }
+                tick(4);   // [4] EA: work
             };
             // stage-B accumulator -> bf16 -> global: thread (n = 4i + quad, d = lane) owns the 32 rows t = N2*m1 + n, m1 = 32h .. 32h+31;
             // a warp store covers 32 channels = 64 contiguous bytes
@@ -597,6 +672,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
             auto epilogueB = [&](int i) {
                 const uint32_t u = gi0 + i, p = u & 1u;
                 mbar_wait_tc(&bars->db_full[p], (u >> 1) & 1u, dbg, 18u, u);
+                tick(5);   // [5] EB: wait for the stage-B MMA
                 tc_fence_after();
                 uint32_t v[32];
                 tmem_ld32(tq + COL_D1 + 64u * p + 32u * h, v);
@@ -607,6 +683,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 __nv_bfloat16* o = obase + (size_t)(4 * i) * prm.D;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) stg_bf16(o + (size_t)j * row_stride, __uint_as_float(v[j]));
+                tick(6);   // [6] EB: work
             };
             epilogueA(0);
             for (int c = 1; c < NCH; ++c) {
@@ -614,6 +691,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
                 epilogueB(2 * (c - 1) + tp);
             }
             epilogueB(2 * (NCH - 1) + tp);
+            mark(it, 3);
+            if (timing && lane == 0 && it < 8) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) reinterpret_cast<volatile uint64_t*>(dbg + 1024 + 64)[it * 8 + q] = tacc[q];
+            }
         }
         // ---- end of the work item: every role has drained; the aliased buffers and TMEM columns change hands ----
         tc_fence_before();

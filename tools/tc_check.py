@@ -80,6 +80,10 @@ def child(B, T, D, Fn):
         res[name] = e0.elapsed_time(e1) / 20
     res["ok"] = all(res[n] <= 1e-2 for n in ("y", "gx", "gw_re", "gw_im", "gb"))
     print(json.dumps(res))
+    if os.environ.get("SML_DEBUG") and os.environ.get("SML_TC") == "1":
+        fwd(); torch.cuda.synchronize()
+        sys.stderr.write("timeline of one forward launch:\n"); sys.stderr.flush()
+        lib.sml_debug_dump()
 
 
 def main():
@@ -98,13 +102,18 @@ def main():
         return
     bad = 0
     for tc in (("1",) if "--tc-only" in sys.argv else ("1", "0")):
-        env = dict(os.environ, SML_TC=tc, SML_DEBUG="1")
+        env = dict(os.environ, SML_TC=tc)
+        if not os.environ.get("SML_NO_DEBUG"):
+            env["SML_DEBUG"] = "1"
         for (B, T, D, Fn) in SHAPES:
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), str(B), str(T), str(D), str(Fn)], env=env, capture_output=True,
                                    text=True, timeout=180)
                 out = r.stdout.strip().splitlines()
                 print(f"SML_TC={tc}", out[-1] if out else "", flush=True)
+                tl = [ln for ln in (r.stderr or "").splitlines() if "tc timeline" in ln]
+                if tl:
+                    print("\n".join(tl[:8]), flush=True)
                 if r.returncode != 0:
                     bad += 1
                     print("   exit", r.returncode, (r.stderr or "")[-1500:], flush=True)
