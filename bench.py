@@ -307,6 +307,14 @@ class Problem:
             self.layer.bias.normal_()
         self.x = torch.randn(B, T, D, device=dev).to(self.dtype)
         self.g = torch.randn(B, T, D, device=dev).to(self.dtype)
+        if world > 1 and os.environ.get("SML_ALLREDUCE", "symm") != "nccl":
+            # filter/bias gradients written straight into an NVLink symmetric-memory bucket and summed in place (multimem);
+            # any failure to set it up leaves the NCCL all-reduce in place
+            try:
+                from tensor_cuda_fft_b200 import attach_symmetric_grad_buffers
+                attach_symmetric_grad_buffers([self.layer])
+            except Exception as e:
+                sys.stderr.write(f"symmetric-memory gradient bucket unavailable ({str(e).splitlines()[0][:160]}): using NCCL\n")
 
     def step(self):
         """forward + backward through the module API (autograd included); at N > 1 one flat all-reduce of the filter gradients."""
@@ -561,6 +569,10 @@ def run_e2e(prob, args, world, dev, barrier, max_over_ranks):
     from tensor_cuda_fft_b200 import spectral_mix_fwd_bwd_host
     B, T, D, dtype, esz = prob.B, prob.T, prob.D, prob.dtype, prob.esz
     param_bytes = (2 * D * prob.Fn + D) * 4
+    # the host side of this leg is PCIe/host-memory bound: sit on the GPU's NUMA node BEFORE the pinned buffers are touched
+    from tensor_cuda_fft_b200.distributed import bind_to_gpu_numa_node
+    old_affinity = os.sched_getaffinity(0)      # restored at the end of the leg: the CPU baseline wants every core again
+    numa = bind_to_gpu_numa_node(dev.index) if os.environ.get("SML_NUMA_BIND", "1") != "0" else {"how": "disabled (SML_NUMA_BIND=0)"}
     xh = torch.empty(B, T, D, dtype=dtype).pin_memory()
     gh = torch.empty(B, T, D, dtype=dtype).pin_memory()
     xh.copy_(prob.x.detach())
@@ -586,10 +598,15 @@ def run_e2e(prob, args, world, dev, barrier, max_over_ranks):
         e2e_step()
     torch.cuda.synchronize()
     ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_e2e
+    try:
+        os.sched_setaffinity(0, old_affinity)
+    except Exception:
+        pass
     return {"value": world * B * T / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B * T * D * esz + param_bytes,
             "d2h_bytes_per_step": 2 * B * T * D * esz + param_bytes, "ms_per_step": ms, "steps": n_e2e,
             "api": "sml_fwd_bwd_host (C ABI, host pointers): pinned host x,g,params in; y, gx, filter/bias grads out; "
-                   "batch-chunked H2D / kernels / D2H pipeline on three streams"}
+                   "batch-chunked H2D / kernels / D2H pipeline on three streams",
+            "host_affinity": numa}
 
 
 def run_sweep(args, dev, rank, world, barrier, max_over_ranks, roof):

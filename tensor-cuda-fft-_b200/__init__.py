@@ -7,12 +7,12 @@ from .spectral_layers import (HybridSpectralAttention, SpectralMLPBlock, Spectra
                               spectral_mix_fwd_bwd_host)
 from .wirtinger_ops import (ComplexParameter, WirtingerGradient, WirtingerSpectralFilter)
 from .byte_spectral_model import ByteSpectralEmbedding, SpectralLanguageModel
-from .distributed import allreduce_filter_grads, shard_batch
+from .distributed import allreduce_filter_grads, attach_symmetric_grad_buffers, shard_batch
 
 __version__ = "0.1.0"
 __all__ = [
     "SpectralMixingLayer", "SpectralMLPBlock", "HybridSpectralAttention", "spectral_mix", "spectral_mix_fwd_bwd_host",
     "WirtingerGradient", "ComplexParameter", "WirtingerSpectralFilter",
     "ByteSpectralEmbedding", "SpectralLanguageModel",
-    "allreduce_filter_grads", "shard_batch",
+    "allreduce_filter_grads", "attach_symmetric_grad_buffers", "shard_batch",
 ]

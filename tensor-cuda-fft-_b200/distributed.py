@@ -36,6 +36,57 @@ def filter_grad_tensors(modules: Iterable[torch.nn.Module]) -> List[torch.Tensor
     return [p.grad for p in filter_grad_params(modules)]
 
 
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: Optional[int] = None, local_rank: Optional[int] = None,
+                          local_world_size: Optional[int] = None) -> dict:
+    """Pin the calling process to the CPU cores of its GPU's NUMA node (sysfs: /sys/bus/pci/devices/<bdf>/numa_node), so that
+    the pinned host buffers it allocates AFTERWARDS (first touch) and the threads that fill them sit next to the GPU's PCIe
+    root -- what the host-buffer path (sml_fwd_bwd_host) needs when 8 ranks stream at once.  Where the platform exposes no
+    node (virtualised hosts report -1) the available cores are split evenly over the local ranks instead.
+    Returns a record of what was done (bench.py puts it into the e2e object)."""
+    info = {"numa_node": None, "cpus": None, "how": "unchanged"}
+    try:
+        import torch
+        idx = torch.cuda.current_device() if device_index is None else device_index
+        pr = torch.cuda.get_device_properties(idx)
+        bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = -1
+        try:
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        except Exception:
+            pass
+        avail = sorted(os.sched_getaffinity(0))
+        cpus: List[int] = []
+        if node >= 0:
+            try:
+                cpus = [c for c in _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) if c in avail]
+            except Exception:
+                cpus = []
+            info["how"] = f"sysfs numa_node of {bdf}"
+        if not cpus:
+            lr = int(os.environ.get("LOCAL_RANK", "0")) if local_rank is None else local_rank
+            lw = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))) if local_world_size is None else local_world_size
+            if lw > 1 and len(avail) >= lw:
+                per = len(avail) // lw
+                cpus = avail[lr * per: (lr + 1) * per]
+                info["how"] = f"no NUMA node exposed for {bdf}: even split of {len(avail)} cores over {lw} local ranks"
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["numa_node"], info["cpus"] = node, f"{cpus[0]}-{cpus[-1]} ({len(cpus)})"
+    except Exception as e:   # never fatal: affinity is an optimisation
+        info["how"] = f"failed: {e!r}"[:160]
+    return info
+
+
 LAST_ALLREDUCE_PATH = "none"     # "symm_mem multimem" | "symm_mem one_shot" | "nccl" -- what the last call used (bench.py reports it)
 
 
@@ -76,6 +127,64 @@ class _SymmetricAllReduce:
             flat.copy_(torch.ops.symm_mem.one_shot_all_reduce(self.buf, "sum", self.group_name))
 
 
+class SymmetricGradBucket:
+    """One NVLink/NVSwitch symmetric-memory allocation holding the [weight_real.grad | weight_imag.grad | bias.grad] blocks of
+    a set of SpectralMixingLayer modules back to back.  Each module's backward writes its filter/bias gradient STRAIGHT into
+    its slice (``module._grad_buffer``, picked up by the autograd function), so the cross-rank sum is ONE in-place multimem
+    all-reduce over the bucket -- in-switch reduction (NVLS) when the fabric has multicast, peer reads otherwise -- with no
+    staging copy on either side and no NCCL launch.  ``param.grad`` tensors are views of the bucket (DDP's
+    gradient_as_bucket_view): consume them (optimizer step) before the next backward overwrites them."""
+
+    def __init__(self, modules, group=None, allocator=None):
+        self.modules = [m for m in modules if getattr(m, "weight_real", None) is not None]
+        if not self.modules:
+            raise ValueError("no learnable SpectralMixingLayer modules given")
+        self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
+        sizes = [2 * m.weight_real.numel() + m.bias.numel() for m in self.modules]
+        device = self.modules[0].weight_real.device
+        self.numel = sum(sizes)
+        self.multicast = False
+        self.group_name = None
+        if allocator is not None:                      # tests: any tensor factory
+            self.buf = allocator(self.numel, device)
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.group_name = self.group.group_name
+            self.buf = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(self.buf, self.group_name)
+            self.multicast = bool(getattr(hdl, "multicast_ptr", 0))
+        off = 0
+        for m, n in zip(self.modules, sizes):
+            m._grad_buffer = self.buf[off: off + n]
+            off += n
+
+    def covers(self, grads: List[torch.Tensor]) -> bool:
+        """True if every gradient is a view into this bucket (then one collective over the bucket sums all of them)."""
+        base = self.buf.untyped_storage().data_ptr()
+        return all(g.is_contiguous() and g.untyped_storage().data_ptr() == base for g in grads)
+
+    def all_reduce(self) -> str:
+        if self.group_name is None:
+            raise RuntimeError("bucket was built with a test allocator: no collective available")
+        if self.multicast:
+            torch.ops.symm_mem.multimem_all_reduce_(self.buf, "sum", self.group_name)
+            return "symm_mem multimem in place"
+        torch.ops.symm_mem.two_shot_all_reduce_(self.buf, "sum", self.group_name)
+        return "symm_mem two_shot in place"
+
+
+_BUCKETS: List["SymmetricGradBucket"] = []
+
+
+def attach_symmetric_grad_buffers(modules: Iterable[torch.nn.Module], group: Optional[dist.ProcessGroup] = None,
+                                  allocator=None) -> SymmetricGradBucket:
+    """Give the modules' filter/bias gradients a home in NVLink symmetric memory (see SymmetricGradBucket).  Call once after the
+    process group is up; ``allreduce_filter_grads`` then reduces the bucket in place."""
+    bucket = SymmetricGradBucket(list(modules), group, allocator)
+    _BUCKETS.append(bucket)
+    return bucket
+
+
 def _flat_view(grads: List[torch.Tensor]) -> Optional[torch.Tensor]:
     """If the gradients are contiguous, back-to-back slices of one storage (the layout sml_backward writes), return a
     1-D view covering all of them (no copy); else None."""
@@ -108,6 +217,17 @@ def allreduce_filter_grads(modules: Iterable[torch.nn.Module], group: Optional[d
     if not params:
         return None
     grads = [p.grad for p in params]
+    global LAST_ALLREDUCE_PATH
+    if not async_op:
+        for bucket in _BUCKETS:      # gradients written straight into a symmetric-memory bucket: one in-place collective
+            if bucket.group_name is not None and bucket.covers(grads):
+                try:
+                    LAST_ALLREDUCE_PATH = bucket.all_reduce()
+                    if average:
+                        bucket.buf.div_(dist.get_world_size(group))
+                    return None
+                except Exception as e:   # pragma: no cover - an op missing from this torch build: fall through to NCCL
+                    bucket.group_name, bucket.err = None, repr(e)
     flat = _flat_view(grads)
     in_place = flat is not None       # the fused backward hands out views of ONE flat [gw_re | gw_im | gb] buffer
     if flat is None:
@@ -122,7 +242,6 @@ def allreduce_filter_grads(modules: Iterable[torch.nn.Module], group: Optional[d
     use_symm = mode == "symm"
     if flat.is_cuda and not async_op and flat.dtype == torch.float32 and use_symm:
         symm = _SymmetricAllReduce.get(flat.numel(), flat.device, group if group is not None else dist.group.WORLD)
-    global LAST_ALLREDUCE_PATH
     done = False
     if symm is not None and symm.ok:
         try:

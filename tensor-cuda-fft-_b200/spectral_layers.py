@@ -69,7 +69,7 @@ class _SpectralMixFn(torch.autograd.Function):
     (== WirtingerGradient.backward, wirtinger_ops.py:53-82) computed by sml_backward."""
 
     @staticmethod
-    def forward(ctx, x, w_re, w_im, bias):
+    def forward(ctx, x, w_re, w_im, bias, grad_buffer=None):
         if not x.is_cuda:
             raise RuntimeError("SpectralMixingLayer (B200 build) needs a CUDA tensor; there is no CPU path")
         if x.dtype not in _IO_DTYPES:
@@ -103,6 +103,7 @@ class _SpectralMixFn(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.fast_path = fast_path
         ctx.param_dtypes = (w_re.dtype, w_im.dtype, None if bias is None else bias.dtype)
+        ctx.grad_buffer = grad_buffer
         return y
 
     @staticmethod
@@ -121,8 +122,14 @@ class _SpectralMixFn(torch.autograd.Function):
         flat = None
         gwr = gwi = gb = None
         if want:
-            # one flat buffer [gw_re | gw_im | gb] so a data-parallel job can all-reduce it in a single call
-            flat = torch.empty(2 * D * Fn + D, dtype=torch.float32, device=gc.device)
+            # one flat buffer [gw_re | gw_im | gb] so a data-parallel job can all-reduce it in a single call.  A caller-provided
+            # buffer (distributed.attach_symmetric_grad_buffers: a slice of an NVLink symmetric-memory bucket) makes the
+            # reduction kernel's own store the collective's input: no copy in, no copy out.
+            gbuf = ctx.grad_buffer
+            if gbuf is not None and gbuf.device == gc.device and gbuf.numel() == 2 * D * Fn + D and gbuf.dtype == torch.float32:
+                flat = gbuf
+            else:
+                flat = torch.empty(2 * D * Fn + D, dtype=torch.float32, device=gc.device)
             gwr = flat[: D * Fn].view(D, Fn)
             gwi = flat[D * Fn: 2 * D * Fn].view(D, Fn)
             gb = flat[2 * D * Fn:]
@@ -137,7 +144,8 @@ class _SpectralMixFn(torch.autograd.Function):
         return (gx if need[0] else None,
                 gwr.to(dt[0]) if (want and need[1]) else None,
                 gwi.to(dt[1]) if (want and need[2]) else None,
-                gb.to(dt[2]) if (want and ctx.has_bias and need[3]) else None)
+                gb.to(dt[2]) if (want and ctx.has_bias and need[3]) else None,
+                None)
 
 
 def spectral_mix(x: torch.Tensor, weight_real: torch.Tensor, weight_imag: torch.Tensor,
@@ -215,7 +223,7 @@ class SpectralMixingLayer(nn.Module):
                     raise RuntimeError("SpectralMixingLayer (B200 build) needs a CUDA tensor; there is no CPU path")
                 y = x + 0.0 * (self.weight_real.sum() + self.weight_imag.sum() + self.bias.sum()).to(x.dtype)
             else:
-                y = _SpectralMixFn.apply(x, self.weight_real, self.weight_imag, self.bias)
+                y = _SpectralMixFn.apply(x, self.weight_real, self.weight_imag, self.bias, getattr(self, "_grad_buffer", None))
         else:
             # learnable=False is fft followed by ifft(.).real (spectral_layers.py:88, :112): the identity up to
             # rounding (reference self-test :301-309 measures 1.2e-7); returned exactly, as a new tensor.

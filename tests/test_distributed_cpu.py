@@ -73,3 +73,18 @@ def test_sharded_filter_grad_allreduce(flat_layout):
         assert torch.allclose(gb, want_b, atol=1e-5)
         assert torch.allclose(gwr, want_b.unsqueeze(1).repeat(1, 3), atol=1e-5)
         assert torch.allclose(gwi, 2 * want_b.unsqueeze(1).repeat(1, 3), atol=1e-5)
+
+
+def test_symmetric_grad_bucket_layout_cpu():
+    """SymmetricGradBucket hands every module a slice of ONE flat buffer laid out [gw_re | gw_im | gb] per module, back to back
+    (the buffer is NVLink symmetric memory on a GPU job; here a plain tensor through the test allocator)."""
+    import torch
+    from tensor_cuda_fft_b200 import SpectralMixingLayer
+    from tensor_cuda_fft_b200.distributed import SymmetricGradBucket
+    mods = [SpectralMixingLayer(8), SpectralMixingLayer(16, num_filters=4), SpectralMixingLayer(6, learnable=False)]
+    bucket = SymmetricGradBucket(mods, group=None, allocator=lambda n, dev: torch.zeros(n, device=dev))
+    assert bucket.numel == (2 * 8 * 4 + 8) + (2 * 16 * 4 + 16)
+    assert mods[0]._grad_buffer.numel() == 72 and mods[1]._grad_buffer.numel() == 144 and not hasattr(mods[2], "_grad_buffer")
+    assert mods[1]._grad_buffer.data_ptr() == bucket.buf.data_ptr() + 72 * 4
+    views = [mods[0]._grad_buffer[:32].view(8, 4), mods[1]._grad_buffer[128:]]
+    assert bucket.covers(views) and not bucket.covers([torch.zeros(3)])
