@@ -712,7 +712,8 @@ def test_full_size_filter_gradients(pkg, dev, B, T, D, dtype):
     got_re, got_im = layer.weight_real.grad.double(), layer.weight_imag.grad.double()
     assert orc.rel_l2(got_re[:, :k].cpu().numpy(), want_re.cpu().numpy()) <= tol
     assert orc.rel_l2(got_im[:, :k].cpu().numpy(), want_im.cpu().numpy()) <= tol
-    assert got_re[:, k:].abs().max().item() == 0.0 and got_im[:, k:].abs().max().item() == 0.0      # columns >= k are dense zeros
+    if k < Fn:      # columns >= k are dense zeros
+        assert got_re[:, k:].abs().max().item() == 0.0 and got_im[:, k:].abs().max().item() == 0.0
     assert orc.rel_l2(layer.bias.grad.double().cpu().numpy(), g.double().sum(dim=(0, 1)).cpu().numpy()) <= tol
 
 
