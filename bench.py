@@ -307,12 +307,14 @@ class Problem:
             self.layer.bias.normal_()
         self.x = torch.randn(B, T, D, device=dev).to(self.dtype)
         self.g = torch.randn(B, T, D, device=dev).to(self.dtype)
-        if world > 1 and os.environ.get("SML_ALLREDUCE", "symm") != "nccl":
-            # filter/bias gradients written straight into an NVLink symmetric-memory bucket and summed in place (multimem);
-            # any failure to set it up leaves the NCCL all-reduce in place
+        mode = os.environ.get("SML_ALLREDUCE", "fused")
+        if world > 1 and mode != "nccl":
+            # filter/bias gradients live in an NVLink symmetric-memory bucket: "fused" (default) = the batch-reduction kernel pushes
+            # its sums with multimem.red, the all-reduce is that store plus one barrier; "symm" = local sums + one in-place multimem
+            # all-reduce; any failure to set it up leaves the NCCL all-reduce in place
             try:
                 from tensor_cuda_fft_b200 import attach_symmetric_grad_buffers
-                attach_symmetric_grad_buffers([self.layer])
+                attach_symmetric_grad_buffers([self.layer], fused=None if mode == "fused" else False)
             except Exception as e:
                 sys.stderr.write(f"symmetric-memory gradient bucket unavailable ({str(e).splitlines()[0][:160]}): using NCCL\n")
 

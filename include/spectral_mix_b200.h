@@ -68,6 +68,20 @@ int sml_backward(const void* g, const void* xlow, const float* w_re, const float
                  float* gw_re, float* gw_im, float* gb, void* workspace, size_t workspace_bytes, int B, int T,
                  int D, int F, int io_dtype, void* stream);
 
+/* Backward whose batch reduction IS the data-parallel all-reduce (the one collective of the path: the filter/bias gradient
+ * sum over ranks, the cross-rank continuation of wirtinger_ops.py:77-80; the reference itself has no distributed code).
+ * Same as sml_backward, except that gw_re | gw_im | gb must be the three blocks of ONE flat fp32 buffer (gw_im = gw_re + D*F,
+ * gb = gw_re + 2*D*F) that lives in NVLink symmetric memory on every rank of the job, and
+ *   flat_multicast = the MULTICAST alias of that flat buffer (NVSwitch multicast object mapped on all ranks),
+ *   flat_next      = this rank's LOCAL copy of the flat buffer of the other parity (cleared here for the next step).
+ * The reduction kernel pushes its sums with multimem.red.add: the switch adds them into every rank's copy.  The caller
+ * (1) keeps two flat buffers and alternates them step by step, both zero before the first use, (2) runs a cross-rank barrier
+ * on the stream after the backward of every layer that shares the buffer; after it gw_* / gb hold the sum over all ranks.
+ * Fused kernels only (an unsupported shape is an error); not bitwise reproducible (the switch picks the summation order). */
+int sml_backward_allreduce(const void* g, const void* xlow, const float* w_re, const float* w_im, void* gx,
+                           float* gw_re, float* gw_im, float* gb, void* workspace, size_t workspace_bytes, int B,
+                           int T, int D, int F, int io_dtype, void* flat_multicast, void* flat_next, void* stream);
+
 /* Forward + backward over HOST buffers (pinned memory recommended: pageable memory serialises the copies).
  * Same math as sml_forward followed by sml_backward, for hosts whose activations live in CPU memory: the batch is cut
  * into chunks of `chunk_batch` elements (0 = choose) and the host->device copy of chunk i+1, the two kernels of

@@ -59,6 +59,8 @@ def _declare(lib):
     lib.sml_forward.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_void_p]
     lib.sml_backward.restype = c_int
     lib.sml_backward.argtypes = [c_void_p] * 9 + [c_size_t] + [c_int] * 5 + [c_void_p]
+    lib.sml_backward_allreduce.restype = c_int
+    lib.sml_backward_allreduce.argtypes = [c_void_p] * 9 + [c_size_t] + [c_int] * 5 + [c_void_p] * 3
     lib.sml_fwd_bwd_host.restype = c_int
     lib.sml_fwd_bwd_host.argtypes = [c_void_p] * 10 + [c_int] * 6
     lib.sml_host_release.restype = c_int
@@ -80,7 +82,7 @@ EXPORTED_SYMBOLS = (
     "sml_forward", "sml_backward", "sml_fwd_bwd_host", "sml_host_release",
     "sml_wirtinger_mul_forward", "sml_wirtinger_mul_backward",
     "sml_wirtinger_filter_forward", "sml_wirtinger_filter_backward",
-    "sml_launch_count", "sml_debug_dump", "sml_release",
+    "sml_launch_count", "sml_debug_dump", "sml_release", "sml_backward_allreduce",
 )
 
 

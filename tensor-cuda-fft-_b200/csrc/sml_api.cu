@@ -278,7 +278,7 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
 template <typename IO>
 int backward_impl(const void* g, const void* xlow, const float* w_re, const float* w_im, void* gx, float* gw_re,
                   float* gw_im, float* gb, void* ws, size_t ws_bytes, int B, int T, int D, int F, int io_dtype,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, float* flat_mc = nullptr, float* flat_next = nullptr) {
     DeviceState* st;
     if (device_state(&st, nullptr)) return 1;
     if (st->cc_major != 10) return fail("libspectral_mix_b200 is built for sm_100a only (device is sm_%d*)", st->cc_major * 10);
@@ -290,6 +290,12 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
     if (twiddle_table(st, T, stream, &gtab)) return 1;
     const float invT = 1.0f / (float)T;
     const bool aligned = ((uintptr_t)g % 16 == 0) && ((uintptr_t)gx % 16 == 0);
+    if (flat_mc != nullptr) {
+        if (!(p.path == SML_PATH_FAST && aligned)) return fail("the fused reduce + all-reduce needs the fused kernels (T a multiple of 64, 16-byte aligned activations)");
+        if (!want_grads || flat_next == nullptr) return fail("the fused reduce + all-reduce needs gw_re/gw_im/gb and the next-parity buffer");
+        if (gw_im != gw_re + (size_t)D * F || gb != gw_re + 2 * (size_t)D * F)
+            return fail("the fused reduce + all-reduce needs gw_re | gw_im | gb back to back in one flat buffer");
+    }
     if (p.path == SML_PATH_FAST && aligned) {
         const size_t part_bytes = sizeof(sml::cf) * (size_t)B * D * (size_t)p.k;
         const size_t need_ws = part_bytes + sizeof(float) * (size_t)B * D;
@@ -308,7 +314,8 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
             if (want_grads) {
                 const long long n = (long long)D * ((F + 1) / 2);
                 SML_CUDA(sml_host::launch_pdl(sml::filtergrad_reduce_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
-                                              reinterpret_cast<const float2*>(gpart), (const float*)gbpart, gw_re, gw_im, gb, B, D, F, p.k));
+                                              reinterpret_cast<const float2*>(gpart), (const float*)gbpart, gw_re, gw_im, gb, B, D, F, p.k,
+                                              flat_mc, flat_next));
                 count_launch();
             }
             return 0;
@@ -334,7 +341,8 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         if (want_grads) {
             const long long n = (long long)D * ((F + 1) / 2);
             SML_CUDA(sml_host::launch_pdl(sml::filtergrad_reduce_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
-                                          reinterpret_cast<const float2*>(prm.gpart), (const float*)prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k));
+                                          reinterpret_cast<const float2*>(prm.gpart), (const float*)prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k,
+                                          flat_mc, flat_next));
             count_launch();
         }
         return 0;
@@ -649,6 +657,20 @@ int sml_backward(const void* g, const void* xlow, const float* w_re, const float
                                     io_dtype, (cudaStream_t)stream);
     return backward_impl<__nv_bfloat16>(g, xlow, w_re, w_im, gx, gw_re, gw_im, gb, workspace, workspace_bytes, B, T, D,
                                         F, io_dtype, (cudaStream_t)stream);
+}
+
+int sml_backward_allreduce(const void* g, const void* xlow, const float* w_re, const float* w_im, void* gx, float* gw_re,
+                           float* gw_im, float* gb, void* workspace, size_t workspace_bytes, int B, int T, int D, int F,
+                           int io_dtype, void* flat_multicast, void* flat_next, void* stream) {
+    if (check_common(g, gx, B, T, D, F, io_dtype)) return 1;
+    if (w_re == nullptr || w_im == nullptr) return fail("null filter pointer");
+    if (flat_multicast == nullptr) return fail("null multicast pointer");
+    g_err[0] = 0;
+    if (io_dtype == SML_DTYPE_F32)
+        return backward_impl<float>(g, xlow, w_re, w_im, gx, gw_re, gw_im, gb, workspace, workspace_bytes, B, T, D, F, io_dtype,
+                                    (cudaStream_t)stream, (float*)flat_multicast, (float*)flat_next);
+    return backward_impl<__nv_bfloat16>(g, xlow, w_re, w_im, gx, gw_re, gw_im, gb, workspace, workspace_bytes, B, T, D, F,
+                                        io_dtype, (cudaStream_t)stream, (float*)flat_multicast, (float*)flat_next);
 }
 
 int sml_fwd_bwd_host(const void* x, const void* g, const float* w_re, const float* w_im, const float* bias, void* y,

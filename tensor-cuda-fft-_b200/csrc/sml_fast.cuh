@@ -577,9 +577,18 @@ __global__ void __launch_bounds__(NR* P, MINB)
 // batch reduction of the filter / bias gradient terms written by the BWD kernel (wirtinger_ops.py:77-80: sum over dim 0).
 // One thread per (d, pair of bins f, f+1 < F) -- pairs that are not both live or not 16-byte aligned take the scalar tail; also zero-fills the columns f >= k, so no memset is needed.
 // Deterministic (fixed summation order over b).
+// Fused collective (mc != null): gw_re / gw_im / gb are the three blocks of ONE flat buffer that lives in NVLink symmetric
+// memory, `mc` is the MULTICAST alias of that buffer: instead of storing its sums locally the kernel pushes them with
+// multimem.red.add -- the NVSwitch adds the value into every rank's copy (in-switch reduction, NVLS) -- so after a
+// cross-rank barrier every rank holds the global sum: the batch reduction's own store IS the all-reduce.  The buffers
+// alternate between two parities; `znext` (the local copy of the other parity) is cleared here for the next step.
+__device__ __forceinline__ void multimem_red_add(float* mc_addr, float v) {
+    asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+}
 static __global__ void __launch_bounds__(256) filtergrad_reduce_kernel(const float2* __restrict__ gpart, const float* __restrict__ gbpart,
                                                 float* __restrict__ gw_re, float* __restrict__ gw_im,
-                                                float* __restrict__ gb, int B, int D, int F, int k) {
+                                                float* __restrict__ gb, int B, int D, int F, int k,
+                                                float* __restrict__ mc, float* __restrict__ znext) {
     // block (64, 4): threadIdx.x -> pair of bins, threadIdx.y -> every 4th batch element; the four partial sums are combined
     // through shared memory in a fixed order (b-slices 0, 1, 2, 3), so the result does not depend on scheduling
     __shared__ float4 part[3][64];
@@ -616,16 +625,30 @@ static __global__ void __launch_bounds__(256) filtergrad_reduce_kernel(const flo
         sr0 += q.x; si0 += q.y; sr1 += q.z; si1 += q.w;
     }
     const size_t o = (size_t)d * F + f;
-    gw_re[o] = sr0;
-    gw_im[o] = si0;
-    if (f + 1 < F) {
-        gw_re[o + 1] = sr1;
-        gw_im[o + 1] = si1;
+    if (mc == nullptr) {
+        gw_re[o] = sr0;
+        gw_im[o] = si0;
+        if (f + 1 < F) {
+            gw_re[o + 1] = sr1;
+            gw_im[o + 1] = si1;
+        }
+    } else {
+        const size_t nW = (size_t)D * F;
+        if (f < k) { multimem_red_add(mc + o, sr0); multimem_red_add(mc + nW + o, si0); }        // columns >= k stay zero
+        if (f + 1 < k) { multimem_red_add(mc + o + 1, sr1); multimem_red_add(mc + nW + o + 1, si1); }
+        znext[o] = 0.f;
+        znext[nW + o] = 0.f;
+        if (f + 1 < F) { znext[o + 1] = 0.f; znext[nW + o + 1] = 0.f; }
     }
     if (f == 0) {
         float sb = 0.f;
         for (int b = 0; b < B; ++b) sb += __ldg(gbpart + (size_t)b * D + d);
-        gb[d] = sb;
+        if (mc == nullptr) {
+            gb[d] = sb;
+        } else {
+            multimem_red_add(mc + 2 * (size_t)D * F + d, sb);
+            znext[2 * (size_t)D * F + d] = 0.f;
+        }
     }
 }
 

@@ -128,59 +128,95 @@ class _SymmetricAllReduce:
 
 
 class SymmetricGradBucket:
-    """One NVLink/NVSwitch symmetric-memory allocation holding the [weight_real.grad | weight_imag.grad | bias.grad] blocks of
-    a set of SpectralMixingLayer modules back to back.  Each module's backward writes its filter/bias gradient STRAIGHT into
-    its slice (``module._grad_buffer``, picked up by the autograd function), so the cross-rank sum is ONE in-place multimem
-    all-reduce over the bucket -- in-switch reduction (NVLS) when the fabric has multicast, peer reads otherwise -- with no
-    staging copy on either side and no NCCL launch.  ``param.grad`` tensors are views of the bucket (DDP's
-    gradient_as_bucket_view): consume them (optimizer step) before the next backward overwrites them."""
+    """NVLink/NVSwitch symmetric-memory home of the [weight_real.grad | weight_imag.grad | bias.grad] blocks of a set of
+    SpectralMixingLayer modules, back to back.
 
-    def __init__(self, modules, group=None, allocator=None):
+    ``fused=True`` (needs NVSwitch multicast): the batch-reduction kernel of every module's backward pushes its sums with
+    ``multimem.red.add`` into the multicast alias of the bucket (sml_backward_allreduce) -- the switch adds them into every
+    rank's copy -- so the cross-rank sum needs NO collective launch and no second pass over the data: one cross-rank barrier
+    on the stream (``all_reduce()``) and every rank holds the global sum.  Two buffers alternate step by step; each backward
+    clears its slice of the other one for the next step.
+    ``fused=False``: each backward writes its local sums into its slice and ``all_reduce()`` runs one in-place multimem
+    (or two-shot) all-reduce over the bucket.
+
+    ``param.grad`` tensors are views of the bucket (DDP's gradient_as_bucket_view): consume them (optimizer step) before the
+    next backward of the same parity overwrites them, and run exactly ONE backward per all-reduce -- micro-batch gradient
+    accumulation across several backward calls needs plain (unattached) gradients."""
+
+    def __init__(self, modules, group=None, allocator=None, fused: Optional[bool] = None):
         self.modules = [m for m in modules if getattr(m, "weight_real", None) is not None]
         if not self.modules:
             raise ValueError("no learnable SpectralMixingLayer modules given")
         self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
-        sizes = [2 * m.weight_real.numel() + m.bias.numel() for m in self.modules]
+        self.sizes = [2 * m.weight_real.numel() + m.bias.numel() for m in self.modules]
         device = self.modules[0].weight_real.device
-        self.numel = sum(sizes)
+        self.numel = sum(self.sizes)
         self.multicast = False
         self.group_name = None
+        self.parity = 0
+        self.hdls = []
         if allocator is not None:                      # tests: any tensor factory
-            self.buf = allocator(self.numel, device)
+            self.bufs = [allocator(self.numel, device), allocator(self.numel, device)]
+            self.fused = bool(fused)
         else:
             import torch.distributed._symmetric_memory as symm_mem
             self.group_name = self.group.group_name
-            self.buf = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
-            hdl = symm_mem.rendezvous(self.buf, self.group_name)
-            self.multicast = bool(getattr(hdl, "multicast_ptr", 0))
+            self.bufs = [symm_mem.empty(self.numel, dtype=torch.float32, device=device) for _ in range(2)]
+            self.hdls = [symm_mem.rendezvous(b, self.group_name) for b in self.bufs]
+            self.multicast = all(bool(getattr(h, "multicast_ptr", 0)) for h in self.hdls)
+            self.fused = self.multicast if fused is None else (bool(fused) and self.multicast)
+            for b in self.bufs:
+                b.zero_()
+            self.hdls[0].barrier(channel=0)            # nobody pushes into a buffer that a peer has not cleared yet
+        self.buf = self.bufs[0]
         off = 0
-        for m, n in zip(self.modules, sizes):
-            m._grad_buffer = self.buf[off: off + n]
+        self.offsets = []
+        for m, n in zip(self.modules, self.sizes):
+            self.offsets.append(off)
+            m._grad_bucket = (self, len(self.offsets) - 1)
             off += n
 
+    # ---- what the autograd function asks for (spectral_layers._SpectralMixFn.backward) ----
+    def slot(self, index: int):
+        """(flat local slice to write / return views of, multicast address of that slice or 0, local slice of the other parity)."""
+        off, n = self.offsets[index], self.sizes[index]
+        cur, nxt = self.bufs[self.parity], self.bufs[self.parity ^ 1]
+        mc = 0
+        if self.fused and self.hdls:
+            mc = int(self.hdls[self.parity].multicast_ptr) + off * 4
+        return cur[off: off + n], mc, nxt[off: off + n]
+
     def covers(self, grads: List[torch.Tensor]) -> bool:
-        """True if every gradient is a view into this bucket (then one collective over the bucket sums all of them)."""
-        base = self.buf.untyped_storage().data_ptr()
+        """True if every gradient is a view into the current buffer of this bucket (one collective / barrier sums all of them)."""
+        base = self.bufs[self.parity].untyped_storage().data_ptr()
         return all(g.is_contiguous() and g.untyped_storage().data_ptr() == base for g in grads)
 
     def all_reduce(self) -> str:
         if self.group_name is None:
             raise RuntimeError("bucket was built with a test allocator: no collective available")
+        cur = self.parity
+        if self.fused:
+            self.hdls[cur].barrier(channel=0)          # every rank's pushes into this parity have landed
+            self.parity ^= 1
+            return "fused: multimem.red from the batch-reduction kernel + one barrier"
         if self.multicast:
-            torch.ops.symm_mem.multimem_all_reduce_(self.buf, "sum", self.group_name)
-            return "symm_mem multimem in place"
-        torch.ops.symm_mem.two_shot_all_reduce_(self.buf, "sum", self.group_name)
-        return "symm_mem two_shot in place"
+            torch.ops.symm_mem.multimem_all_reduce_(self.bufs[cur], "sum", self.group_name)
+            how = "symm_mem multimem in place"
+        else:
+            torch.ops.symm_mem.two_shot_all_reduce_(self.bufs[cur], "sum", self.group_name)
+            how = "symm_mem two_shot in place"
+        return how
 
 
 _BUCKETS: List["SymmetricGradBucket"] = []
 
 
 def attach_symmetric_grad_buffers(modules: Iterable[torch.nn.Module], group: Optional[dist.ProcessGroup] = None,
-                                  allocator=None) -> SymmetricGradBucket:
+                                  allocator=None, fused: Optional[bool] = None) -> SymmetricGradBucket:
     """Give the modules' filter/bias gradients a home in NVLink symmetric memory (see SymmetricGradBucket).  Call once after the
-    process group is up; ``allreduce_filter_grads`` then reduces the bucket in place."""
-    bucket = SymmetricGradBucket(list(modules), group, allocator)
+    process group is up; ``allreduce_filter_grads`` then finishes the cross-rank sum (a barrier when fused, else one in-place
+    collective)."""
+    bucket = SymmetricGradBucket(list(modules), group, allocator, fused)
     _BUCKETS.append(bucket)
     return bucket
 
@@ -222,9 +258,10 @@ def allreduce_filter_grads(modules: Iterable[torch.nn.Module], group: Optional[d
         for bucket in _BUCKETS:      # gradients written straight into a symmetric-memory bucket: one in-place collective
             if bucket.group_name is not None and bucket.covers(grads):
                 try:
+                    cur = bucket.bufs[bucket.parity]
                     LAST_ALLREDUCE_PATH = bucket.all_reduce()
                     if average:
-                        bucket.buf.div_(dist.get_world_size(group))
+                        cur.div_(dist.get_world_size(group))
                     return None
                 except Exception as e:   # pragma: no cover - an op missing from this torch build: fall through to NCCL
                     bucket.group_name, bucket.err = None, repr(e)

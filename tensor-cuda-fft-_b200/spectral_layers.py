@@ -69,7 +69,7 @@ class _SpectralMixFn(torch.autograd.Function):
     (== WirtingerGradient.backward, wirtinger_ops.py:53-82) computed by sml_backward."""
 
     @staticmethod
-    def forward(ctx, x, w_re, w_im, bias, grad_buffer=None):
+    def forward(ctx, x, w_re, w_im, bias, grad_bucket=None):
         if not x.is_cuda:
             raise RuntimeError("SpectralMixingLayer (B200 build) needs a CUDA tensor; there is no CPU path")
         if x.dtype not in _IO_DTYPES:
@@ -103,7 +103,7 @@ class _SpectralMixFn(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.fast_path = fast_path
         ctx.param_dtypes = (w_re.dtype, w_im.dtype, None if bias is None else bias.dtype)
-        ctx.grad_buffer = grad_buffer
+        ctx.grad_bucket = grad_bucket      # (distributed.SymmetricGradBucket, slot index) or None
         return y
 
     @staticmethod
@@ -125,10 +125,14 @@ class _SpectralMixFn(torch.autograd.Function):
             # one flat buffer [gw_re | gw_im | gb] so a data-parallel job can all-reduce it in a single call.  A caller-provided
             # buffer (distributed.attach_symmetric_grad_buffers: a slice of an NVLink symmetric-memory bucket) makes the
             # reduction kernel's own store the collective's input: no copy in, no copy out.
-            gbuf = ctx.grad_buffer
-            if gbuf is not None and gbuf.device == gc.device and gbuf.numel() == 2 * D * Fn + D and gbuf.dtype == torch.float32:
-                flat = gbuf
-            else:
+            mc_ptr, flat_next = 0, None
+            if ctx.grad_bucket is not None:
+                cand, mc_ptr, flat_next = ctx.grad_bucket[0].slot(ctx.grad_bucket[1])
+                if cand.device == gc.device and cand.numel() == 2 * D * Fn + D and cand.dtype == torch.float32:
+                    flat = cand
+                else:
+                    mc_ptr = 0
+            if flat is None:
                 flat = torch.empty(2 * D * Fn + D, dtype=torch.float32, device=gc.device)
             gwr = flat[: D * Fn].view(D, Fn)
             gwi = flat[D * Fn: 2 * D * Fn].view(D, Fn)
@@ -137,8 +141,20 @@ class _SpectralMixFn(torch.autograd.Function):
         ws_bytes = _shape_info(B, T, D, Fn, io)[2] if (want or not ctx.fast_path) else 0
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gc.device) if ws_bytes else None
         with _on_device(gc.device):
-            _native.check(lib.sml_backward(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gx), _ptr(gwr), _ptr(gwi),
-                                           _ptr(gb), _ptr(ws), ws_bytes, B, T, D, Fn, io, _stream_handle(gc.device)))
+            if want and mc_ptr and ctx.fast_path:
+                # the batch-reduction kernel pushes its sums through the NVSwitch multicast alias of the bucket: its store is the
+                # all-reduce (distributed.SymmetricGradBucket, fused mode); the barrier follows in allreduce_filter_grads
+                _native.check(lib.sml_backward_allreduce(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gx), _ptr(gwr), _ptr(gwi),
+                                                         _ptr(gb), _ptr(ws), ws_bytes, B, T, D, Fn, io, mc_ptr, _ptr(flat_next),
+                                                         _stream_handle(gc.device)))
+            else:
+                _native.check(lib.sml_backward(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gx), _ptr(gwr), _ptr(gwi),
+                                               _ptr(gb), _ptr(ws), ws_bytes, B, T, D, Fn, io, _stream_handle(gc.device)))
+                if want and mc_ptr:
+                    # a shape the fused kernels do not take, inside a fused bucket (whose all_reduce() is only a barrier): sum this
+                    # module's block across ranks right here
+                    import torch.distributed as dist
+                    dist.all_reduce(flat, group=ctx.grad_bucket[0].group)
         need = ctx.needs_input_grad
         dt = ctx.param_dtypes
         return (gx if need[0] else None,
@@ -223,7 +239,7 @@ class SpectralMixingLayer(nn.Module):
                     raise RuntimeError("SpectralMixingLayer (B200 build) needs a CUDA tensor; there is no CPU path")
                 y = x + 0.0 * (self.weight_real.sum() + self.weight_imag.sum() + self.bias.sum()).to(x.dtype)
             else:
-                y = _SpectralMixFn.apply(x, self.weight_real, self.weight_imag, self.bias, getattr(self, "_grad_buffer", None))
+                y = _SpectralMixFn.apply(x, self.weight_real, self.weight_imag, self.bias, getattr(self, "_grad_bucket", None))
         else:
             # learnable=False is fft followed by ifft(.).real (spectral_layers.py:88, :112): the identity up to
             # rounding (reference self-test :301-309 measures 1.2e-7); returned exactly, as a new tensor.

@@ -76,15 +76,20 @@ def test_sharded_filter_grad_allreduce(flat_layout):
 
 
 def test_symmetric_grad_bucket_layout_cpu():
-    """SymmetricGradBucket hands every module a slice of ONE flat buffer laid out [gw_re | gw_im | gb] per module, back to back
-    (the buffer is NVLink symmetric memory on a GPU job; here a plain tensor through the test allocator)."""
+    """SymmetricGradBucket hands every module a slice of ONE flat buffer laid out [gw_re | gw_im | gb] per module, back to back,
+    in two alternating parities (the buffers are NVLink symmetric memory on a GPU job; here plain tensors through the test
+    allocator)."""
     import torch
     from tensor_cuda_fft_b200 import SpectralMixingLayer
     from tensor_cuda_fft_b200.distributed import SymmetricGradBucket
     mods = [SpectralMixingLayer(8), SpectralMixingLayer(16, num_filters=4), SpectralMixingLayer(6, learnable=False)]
     bucket = SymmetricGradBucket(mods, group=None, allocator=lambda n, dev: torch.zeros(n, device=dev))
     assert bucket.numel == (2 * 8 * 4 + 8) + (2 * 16 * 4 + 16)
-    assert mods[0]._grad_buffer.numel() == 72 and mods[1]._grad_buffer.numel() == 144 and not hasattr(mods[2], "_grad_buffer")
-    assert mods[1]._grad_buffer.data_ptr() == bucket.buf.data_ptr() + 72 * 4
-    views = [mods[0]._grad_buffer[:32].view(8, 4), mods[1]._grad_buffer[128:]]
+    assert mods[0]._grad_bucket == (bucket, 0) and mods[1]._grad_bucket == (bucket, 1) and not hasattr(mods[2], "_grad_bucket")
+    cur, mc, nxt = bucket.slot(1)
+    assert cur.numel() == 144 and nxt.numel() == 144 and mc == 0
+    assert cur.data_ptr() == bucket.bufs[0].data_ptr() + 72 * 4 and nxt.data_ptr() == bucket.bufs[1].data_ptr() + 72 * 4
+    views = [bucket.slot(0)[0][:32].view(8, 4), cur[128:]]
     assert bucket.covers(views) and not bucket.covers([torch.zeros(3)])
+    bucket.parity ^= 1
+    assert bucket.slot(1)[0].data_ptr() == bucket.bufs[1].data_ptr() + 72 * 4 and not bucket.covers(views)
