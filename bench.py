@@ -485,7 +485,7 @@ def run_ours(args):
                      "algorithmic_bytes_note": "SURVEY.md 8(d): read g + write gx + filter read + gradients written; X_low and the per-batch partial terms are implementation traffic (implementation_extra_bytes), not counted",
                      "implementation_extra_bytes": prob.bytes_impl_extra(),
                      "traffic": traffic.get("sml_backward"),
-                     "traffic_source": "QUOTED from profiles/traffic.json (ncu --set full capture of this configuration, round 1), not measured in this run" if traffic else None})
+                     "traffic_source": "QUOTED from profiles/traffic.json (ncu --set full capture of this configuration, round 2), not measured in this run" if traffic else None})
     roofline_fwd = roof(prob.bytes_fwd(), fwd_ms)
     roofline_fwd.update({"kernel": "sml_forward (one fused kernel)", "launch_ms": fwd_ms, "launch_ms_min": fwd_min,
                          "algorithmic_bytes": prob.bytes_fwd(), "traffic": traffic.get("sml_forward")})

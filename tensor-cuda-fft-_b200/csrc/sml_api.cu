@@ -275,6 +275,24 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
     return 0;
 }
 
+// batch reduction of the per-batch filter/bias gradient terms (+ the fused multimem all-reduce when flat_mc is given)
+int launch_filtergrad_reduce(const sml::cf* gpart, const float* gbpart, float* gw_re, float* gw_im, float* gb, int B, int D, int F,
+                             int k, float* flat_mc, float* flat_next, cudaStream_t stream) {
+    const bool vec4 = F % 4 == 0 && k % 4 == 0 && ((uintptr_t)gw_re % 16 == 0) && ((uintptr_t)gw_im % 16 == 0) && ((uintptr_t)gpart % 16 == 0) &&
+                      (flat_mc == nullptr || (((uintptr_t)flat_mc % 16 == 0) && ((uintptr_t)flat_next % 16 == 0)));
+    if (vec4) {
+        const long long n = (long long)D * (F / 4);
+        SML_CUDA(sml_host::launch_pdl(sml::filtergrad_reduce4_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
+                                      reinterpret_cast<const float2*>(gpart), gbpart, gw_re, gw_im, gb, B, D, F, k, flat_mc, flat_next));
+    } else {
+        const long long n = (long long)D * ((F + 1) / 2);
+        SML_CUDA(sml_host::launch_pdl(sml::filtergrad_reduce_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
+                                      reinterpret_cast<const float2*>(gpart), gbpart, gw_re, gw_im, gb, B, D, F, k, flat_mc, flat_next));
+    }
+    count_launch();
+    return 0;
+}
+
 template <typename IO>
 int backward_impl(const void* g, const void* xlow, const float* w_re, const float* w_im, void* gx, float* gw_re,
                   float* gw_im, float* gb, void* ws, size_t ws_bytes, int B, int T, int D, int F, int io_dtype,
@@ -311,13 +329,7 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
             a.B = B; a.T = T; a.D = D; a.F = F; a.k = p.k;
             a.dbg = debug_record();
             if (sml_host::launch_tc<true>(g, gx, a, st->sm_count, stream)) return 1;
-            if (want_grads) {
-                const long long n = (long long)D * ((F + 1) / 2);
-                SML_CUDA(sml_host::launch_pdl(sml::filtergrad_reduce_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
-                                              reinterpret_cast<const float2*>(gpart), (const float*)gbpart, gw_re, gw_im, gb, B, D, F, p.k,
-                                              flat_mc, flat_next));
-                count_launch();
-            }
+            if (want_grads && launch_filtergrad_reduce(gpart, gbpart, gw_re, gw_im, gb, B, D, F, p.k, flat_mc, flat_next, stream)) return 1;
             return 0;
         }
         CUtensorMap map, map_out;
@@ -338,13 +350,7 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         const int slots = st->sm_count * p.ctas_per_sm;
         const int grid = prm.ntiles < slots ? prm.ntiles : slots;
         if (launch_fast<IO, true>(p, map, map_out, prm, grid, stream)) return 1;
-        if (want_grads) {
-            const long long n = (long long)D * ((F + 1) / 2);
-            SML_CUDA(sml_host::launch_pdl(sml::filtergrad_reduce_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
-                                          reinterpret_cast<const float2*>(prm.gpart), (const float*)prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k,
-                                          flat_mc, flat_next));
-            count_launch();
-        }
+        if (want_grads && launch_filtergrad_reduce(prm.gpart, prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k, flat_mc, flat_next, stream)) return 1;
         return 0;
     }
     // generic path: G into workspace, then synthesis with conj(W) and the batch reduction

@@ -193,7 +193,8 @@ int launch_tc(const void* in, void* out, const TcLaunch& a, int sm_count, cudaSt
     const int grid = prm.nitems < sm_count ? prm.nitems : sm_count;
     // bring-up aid: SML_TC_DUMP=<file> writes the intermediates of work item 0 of a FORWARD launch (tools/tc_dump_check.py)
     static const char* dump_path = getenv("SML_TC_DUMP");
-    if (dump_path != nullptr && !BWD) {
+    if constexpr (!BWD) {
+    if (dump_path != nullptr) {
         const size_t dump_floats = (size_t)prm.N2 * 2048 * 2 + 2 * 36864;
         SML_CUDA(cudaMalloc(&prm.dump, dump_floats * sizeof(float)));
         SML_CUDA(cudaMemset(prm.dump, 0, dump_floats * sizeof(float)));
@@ -205,7 +206,8 @@ int launch_tc(const void* in, void* out, const TcLaunch& a, int sm_count, cudaSt
         cudaFree(prm.dump);
         return 0;
     }
-    if (!BWD && prm.dbg != nullptr) return launch_tc_inst<BWD, 2>(map_in, prm, grid, smem_bytes, stream);   // SML_DEBUG=1: phase timing of CTA 0
+    if (prm.dbg != nullptr) return launch_tc_inst<BWD, 2>(map_in, prm, grid, smem_bytes, stream);   // SML_DEBUG=1: phase timing of CTA 0
+    }
     return launch_tc_inst<BWD, 0>(map_in, prm, grid, smem_bytes, stream);
 }
 
