@@ -510,6 +510,23 @@ def run_ours(args):
         except Exception as e:   # the sub-record must never cost the headline line
             bf16 = {"unavailable": str(e).splitlines()[0][:200]}
 
+    # ---- launch-bound shapes (configs[0]): the same step replayed from CUDA graphs (SpectralMixingLayer.graphed) ----
+    graphed = None
+    if world == 1 and 2 * B * T * D * prob.esz < 64e6:
+        try:
+            glayer = prob.layer.graphed(prob.x)
+
+            def gstep():
+                prob.layer.zero_grad(set_to_none=True)
+                xr = prob.x.detach().requires_grad_(True)
+                glayer(xr).backward(prob.g)
+
+            ms_g = time_steps(gstep, max(args.steps, 50), 5, barrier)
+            graphed = {"ms_per_step": ms_g, "value": B * T / (ms_g * 1e-3), "unit": UNIT,
+                       "what": "the same fwd+bwd step with forward and backward replayed from CUDA graphs (SpectralMixingLayer.graphed)"}
+        except Exception as e:
+            graphed = {"unavailable": str(e).splitlines()[0][:200]}
+
     # ---- end to end: the reference-facing C-ABI call with HOST buffers (sml_fwd_bwd_host): pinned host x, g in;
     #      y, gx and the filter/bias gradients back in host memory; all copies inside the timed region ----
     e2e = None
@@ -550,7 +567,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_step": roofline_step,
-            "bf16": bf16,
+            "bf16": bf16, "graphed": graphed,
             "e2e": e2e, "cpu_baseline": cpu, "reference_algorithm_on_gpu": gpu_ref,
         }
         print_line(json.dumps(line))

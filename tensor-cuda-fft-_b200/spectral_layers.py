@@ -250,6 +250,18 @@ class SpectralMixingLayer(nn.Module):
             return y
         return self.dropout(y)
 
+    def graphed(self, sample: torch.Tensor, num_warmup_iters: int = 3):
+        """A CUDA-graph-captured callable of this layer for inputs of ``sample``'s shape and dtype (forward AND backward are
+        replayed as graphs: no per-call Python, ctypes or launch work on the host -- what small, launch-bound shapes such as
+        BASELINE configs[0] (8, 512, 256) need).  The warm-up iterations build the per-(device, T) tables, which must exist
+        before capture.  Usual CUDA-graph rules: fixed shape, dropout inactive, outputs live in graph-owned memory."""
+        if not sample.is_cuda:
+            raise RuntimeError("SpectralMixingLayer (B200 build) needs a CUDA tensor; there is no CPU path")
+        if self.training and self.dropout.p > 0.0:
+            raise RuntimeError("graphed(): dropout draws new random numbers per call; use eval() or dropout=0")
+        return torch.cuda.make_graphed_callables(self, (sample.detach().clone().requires_grad_(True),),
+                                                 num_warmup_iters=num_warmup_iters)
+
     def verify_energy_preservation(self, x: torch.Tensor, y: torch.Tensor) -> float:
         """sum(y^2) / (sum(x^2) + 1e-8), spectral_layers.py:122-132."""
         energy_in = torch.sum(x.float() ** 2).item()
