@@ -120,6 +120,65 @@ int sml_wirtinger_filter_backward(const void* g, const void* x_freq, const float
                                   void* gx, float* gw_re, float* gw_im, int B, int T, int D, int F,
                                   void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Extended entry points: the transform with the hosting block's prologue / epilogue fused in (fused kernels only: an
+ * unsupported shape is an error and the caller composes the unfused calls instead).  They serve
+ *   - SpectralMLPBlock.forward  `x + spectral_mix(norm1(x))`                      fft_tensor/spectral_layers.py:161, :185
+ *   - FixedSpectralBlock.forward: pre-LayerNorm, zero-padded causal FFT convolution with a full half-spectrum multiplier
+ *     k_freq[f] * gain[c] * sigmoid(gate_freq)[f] * sigmoid(gate_ctx)[b,c] * mask[f], irfft, keep [:T], + residual
+ *                                                                                 fft_lm/train_fixed_full.py:498-555
+ *   - overlap_save_block_update (chunked inference)                               scripts/generate_chunked_overlap_save.py:78-177
+ * All fields of sml_ext are optional (NULL / 0 = feature off; T_in = T_out = 0 means "T rows").  Geometry is that of the
+ * FORWARD call; sml_backward_ext takes the same struct and swaps the roles (g has the output geometry, gx the input one).
+ */
+typedef struct sml_ext {
+    const void* row_stats;    /* (B, T) float2 {mean, rstd} per TRANSFORM row, {0,0} on zero-padding rows (sml_ln_stats):
+                                 the kernel transforms x^ = (x - mean) * rstd.  Forward only. */
+    const void* residual;     /* (B, T_out, D) io_dtype: added to the output rows.  Forward only. */
+    const float* chan_scale;  /* (B, D): factor on the filtered spectrum of (batch element, channel) */
+    const float* w_nyq;       /* (D,): real weight of the bin T/2 (needs F >= T/2; bins 1..T/2-1 keep the layer's
+                                 Re(ifft(.)) convention, i.e. an irfft multiplier H enters as w = 2 H there, w[0] = H[0]) */
+    const float* sb_re;       /* (D, F) + (D, F) + (D,): "spectral bias" added to X*W (and to the bin T/2) before chan_scale --  */
+    const float* sb_im;       /*   how a LayerNorm beta enters a zero-padded transform: beta[d] * rfft(rect_T_in)[f] * w0[d,f].  */
+    const float* sb_nyq;      /*   Forward only; all three or none (sb_nyq only with w_nyq).                                   */
+    float* x_nyq;             /* (B, D): spectrum at the bin T/2; written by the forward, read by the backward */
+    float* g_nyq;             /* (B, D): backward only: per-batch-element gradient terms of w_nyq (sum over B outside) */
+    int T_in, in_row0;        /* x holds T_in rows; x row i is transform row in_row0 + i; the other transform rows are zero */
+    int T_out, out_row0;      /* y holds T_out rows = transform rows 0 .. T_out-1, the rest is dropped.  out_row0 must be 0 (TMA
+                                 stores cannot start at a negative coordinate): an output window starting at row o is the phase
+                                 ramp w[d,f] *= exp(2 pi i f o / T), w_nyq *= (-1)^o on the filter.  sml_backward_ext
+                                 likewise needs in_row0 == 0. */
+} sml_ext;
+
+/* 0 if sml_forward_ext / sml_backward_ext can run this problem (fused plan, row windows compatible with it); else an error
+ * with the reason in sml_last_error(). */
+int sml_ext_supported(int B, int T, int D, int F, int io_dtype, const sml_ext* ext);
+
+/* sml_forward / sml_backward with the extensions above.  xlow then holds the spectrum of the normalised, zero-padded
+ * input; gw_re / gw_im / gb are the gradients of the arrays that were passed in (the host maps them back onto the block's
+ * own parameters). */
+int sml_forward_ext(const void* x, const float* w_re, const float* w_im, const float* bias, void* y, void* xlow_save,
+                    int B, int T, int D, int F, int io_dtype, const sml_ext* ext, void* stream);
+int sml_backward_ext(const void* g, const void* xlow, const float* w_re, const float* w_im, void* gx, float* gw_re,
+                     float* gw_im, float* gb, void* workspace, size_t workspace_bytes, int B, int T, int D, int F,
+                     int io_dtype, const sml_ext* ext, void* stream);
+
+/* LayerNorm row statistics in the layout sml_ext.row_stats expects: stats (B, T) float2, transform row t <- input row
+ * t - in_row0 of x (B, T_in, D), {0,0} outside.  eps as in torch.nn.LayerNorm (biased variance). */
+int sml_ln_stats(const void* x, void* stats, int B, int T, int T_in, int in_row0, int D, float eps, int io_dtype,
+                 void* stream);
+/* LayerNorm backward (no affine part: gamma / beta fold into the filter) fused with the skip connection's gradient:
+ *   gx = rstd * (gh' - mean_d(gh') - x^ * mean_d(gh' * x^)) + g_res ;  gh' = gh + chan_add[b, :]
+ * gh = dL/dx^ (B, T_in, D); g_res (B, T_in, D) nullable; chan_add (B, D) fp32 nullable: a per-(batch element, channel)
+ * constant on dL/dx^ (the gradient of a mean over the rows: FixedSpectralBlock's pooled context, train_fixed_full.py:531). */
+int sml_ln_backward(const void* gh, const void* x, const void* stats, const void* g_res, const float* chan_add, void* gx,
+                    int B, int T, int T_in, int in_row0, int D, int io_dtype, void* stream);
+
+/* SpectralEMA.scan, fft_lm/spectral_ssm.py:107-125 (update: :78-105): chunks (B, S, F) complex64, state_in (B, F)
+ * complex64 or NULL (zeros), rho / theta (F,) fp32, state_out (B, F) complex64.  mode 0 = "aligned", 1 = "polar". */
+int sml_spectral_ema_scan(const void* chunks, const void* state_in, const float* rho, const float* theta, void* state_out,
+                          int B, int S, int F, int mode, void* stream);
+
 /* Number of kernel launches issued by this library in the calling process so far (bench.py's gpu_launches). */
 unsigned long long sml_launch_count(void);
 

@@ -38,6 +38,22 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
+class SmlExt(ctypes.Structure):
+    """``sml_ext`` of include/spectral_mix_b200.h: optional block prologue / epilogue of the extended entry points."""
+    _fields_ = [("row_stats", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("chan_scale", ctypes.c_void_p),
+                ("w_nyq", ctypes.c_void_p), ("sb_re", ctypes.c_void_p), ("sb_im", ctypes.c_void_p), ("sb_nyq", ctypes.c_void_p),
+                ("x_nyq", ctypes.c_void_p), ("g_nyq", ctypes.c_void_p),
+                ("T_in", ctypes.c_int), ("in_row0", ctypes.c_int), ("T_out", ctypes.c_int), ("out_row0", ctypes.c_int)]
+
+
+def make_ext(row_stats=None, residual=None, chan_scale=None, w_nyq=None, sb_re=None, sb_im=None, sb_nyq=None, x_nyq=None,
+             g_nyq=None, T_in=0, in_row0=0, T_out=0, out_row0=0) -> SmlExt:
+    """Build an ``sml_ext`` from torch tensors (or None).  The caller keeps the tensors alive for the duration of the call."""
+    p = lambda t: None if t is None else t.data_ptr()
+    return SmlExt(p(row_stats), p(residual), p(chan_scale), p(w_nyq), p(sb_re), p(sb_im), p(sb_nyq), p(x_nyq), p(g_nyq),
+                  int(T_in), int(in_row0), int(T_out), int(out_row0))
+
+
 def _declare(lib):
     c_int, c_void_p, c_size_t, c_ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_longlong
     ip = ctypes.POINTER(ctypes.c_int)
@@ -75,6 +91,19 @@ def _declare(lib):
     lib.sml_wirtinger_filter_forward.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
     lib.sml_wirtinger_filter_backward.restype = c_int
     lib.sml_wirtinger_filter_backward.argtypes = [c_void_p] * 7 + [c_int] * 4 + [c_void_p]
+    ext_p = ctypes.POINTER(SmlExt)
+    lib.sml_ext_supported.restype = c_int
+    lib.sml_ext_supported.argtypes = [c_int] * 5 + [ext_p]
+    lib.sml_forward_ext.restype = c_int
+    lib.sml_forward_ext.argtypes = [c_void_p] * 6 + [c_int] * 5 + [ext_p, c_void_p]
+    lib.sml_backward_ext.restype = c_int
+    lib.sml_backward_ext.argtypes = [c_void_p] * 9 + [c_size_t] + [c_int] * 5 + [ext_p, c_void_p]
+    lib.sml_ln_stats.restype = c_int
+    lib.sml_ln_stats.argtypes = [c_void_p] * 2 + [c_int] * 5 + [ctypes.c_float, c_int, c_void_p]
+    lib.sml_ln_backward.restype = c_int
+    lib.sml_ln_backward.argtypes = [c_void_p] * 6 + [c_int] * 6 + [c_void_p]
+    lib.sml_spectral_ema_scan.restype = c_int
+    lib.sml_spectral_ema_scan.argtypes = [c_void_p] * 5 + [c_int] * 4 + [c_void_p]
 
 
 EXPORTED_SYMBOLS = (
@@ -83,6 +112,7 @@ EXPORTED_SYMBOLS = (
     "sml_wirtinger_mul_forward", "sml_wirtinger_mul_backward",
     "sml_wirtinger_filter_forward", "sml_wirtinger_filter_backward",
     "sml_launch_count", "sml_debug_dump", "sml_release", "sml_backward_allreduce",
+    "sml_ext_supported", "sml_forward_ext", "sml_backward_ext", "sml_ln_stats", "sml_ln_backward", "sml_spectral_ema_scan",
 )
 
 

@@ -18,6 +18,7 @@
 #include "sml_host.h"
 #include "sml_generic.cuh"
 #include "sml_wirtinger.cuh"
+#include "sml_block.cuh"
 
 namespace {
 
@@ -71,6 +72,7 @@ using sml_host::EncodeTiledFn;
 using sml_host::get_encode_fn;
 using sml_host::knobs;
 using sml_host::launch_fast;
+using sml_host::launch_fast_ext;
 using sml_host::Plan;
 
 #define SML_CUDA(expr)                                                                         \
@@ -199,12 +201,15 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
 }
 
 // view of a (B, T, D) activation as the 4-D tensor {D, R, M, B}: t = R*m + r
-int encode_act_map(CUtensorMap* map, const void* base, int B, int T, int D, int io_dtype, const Plan& p) {
+// rows (default T): the tensor holds only `rows` rows per batch element (a multiple of R) -- boxes that reach past them are
+// zero-filled on load and clipped on store (row windows of the extended kernels)
+int encode_act_map(CUtensorMap* map, const void* base, int B, int T, int D, int io_dtype, const Plan& p, int rows = -1) {
     EncodeTiledFn enc;
     if (get_encode_fn(&enc)) return 1;
     const cuuint64_t esz = io_dtype == SML_DTYPE_BF16 ? 2 : 4;
-    cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)p.R, (cuuint64_t)p.M, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)D * esz, (cuuint64_t)p.R * D * esz, (cuuint64_t)T * D * esz};
+    if (rows < 0) rows = T;
+    cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)p.R, (cuuint64_t)(rows / p.R), (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)D * esz, (cuuint64_t)p.R * D * esz, (cuuint64_t)rows * D * esz};
     const int boxrows = p.M < 256 ? p.M : 256;
     cuuint32_t box[4] = {(cuuint32_t)(2 * p.P), 1u, (cuuint32_t)boxrows, 1u};
     cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
@@ -373,6 +378,131 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
             count_launch();
         }
     }
+    SML_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// extended fused kernels: block prologue / epilogue around the transform (sml_ext)
+// ------------------------------------------------------------------------------------------------
+struct ExtGeom {
+    int T_in, in_row0, T_out, out_row0;
+};
+// plan of the extended kernels: the fused plan with two CTAs per SM at the largest sub-transform (64 more registers for the
+// prefetched row statistics) and two landing tiles wherever they fit (the residual rows are prefetched through them)
+Plan make_plan_ext(int T, int D, int F, int io_dtype) {
+    Plan p = make_plan(T, D, F, io_dtype);
+    if (p.path != SML_PATH_FAST) return p;
+    p.tc = false;
+    if (p.NR == 32) p.ctas_per_sm = 2;
+    p.xb = 2;
+    if (knobs().fast_xb) p.xb = knobs().fast_xb == 2 ? 2 : 1;
+    return p;
+}
+int ext_check(const Plan& p, int T, int D, const sml_ext* e, ExtGeom* g) {
+    if (p.path != SML_PATH_FAST) return fail("the extended entry points need the fused kernels (T a multiple of 64 that holds the band, 16-byte rows)");
+    g->T_in = e && e->T_in > 0 ? e->T_in : T;
+    g->T_out = e && e->T_out > 0 ? e->T_out : T;
+    g->in_row0 = e ? e->in_row0 : 0;
+    g->out_row0 = e ? e->out_row0 : 0;
+    if (g->in_row0 < 0 || g->out_row0 < 0 || g->in_row0 + g->T_in > T || g->out_row0 + g->T_out > T)
+        return fail("row windows [%d, %d) / [%d, %d) do not fit the transform length %d", g->in_row0, g->in_row0 + g->T_in, g->out_row0,
+                    g->out_row0 + g->T_out, T);
+    if (g->out_row0 != 0)
+        return fail("out_row0 must be 0: TMA stores cannot start at a negative coordinate; shift the output by a phase ramp on the "
+                    "filter instead, w[d,f] *= exp(2 pi i f out_row0 / T), w_nyq *= (-1)^out_row0");
+    if (g->T_in % p.R != 0 || g->T_out % p.R != 0)
+        return fail("T_in = %d and T_out = %d must be multiples of R = %d passes for this plan (pad the buffers)", g->T_in, g->T_out, p.R);
+    if (e && e->w_nyq != nullptr) {
+        if (T % 2 != 0 || p.k != T / 2 || p.k != p.NR * p.KJ)   // the kernel finds the bin at band column KJ of the f1 = 0 lanes
+            return fail("w_nyq needs a full half-spectrum filter (F >= T/2, T even) on a plan that carries the bin T/2");
+    }
+    return 0;
+}
+
+template <typename IO, bool BWD>
+int ext_impl(const void* in, const float* w_re, const float* w_im, const float* bias, void* out, void* xlow, float* gw_re,
+             float* gw_im, float* gb, void* ws, size_t ws_bytes, int B, int T, int D, int F, int io_dtype, const sml_ext* e,
+             cudaStream_t stream) {
+    DeviceState* st;
+    if (device_state(&st, nullptr)) return 1;
+    if (st->cc_major != 10) return fail("libspectral_mix_b200 is built for sm_100a only (device is sm_%d*)", st->cc_major * 10);
+    const Plan p = make_plan_ext(T, D, F, io_dtype);
+    ExtGeom g;
+    if (ext_check(p, T, D, e, &g)) return 1;
+    if (((uintptr_t)in % 16) || ((uintptr_t)out % 16) || (e && e->residual && ((uintptr_t)e->residual % 16)))
+        return fail("the extended entry points need 16-byte aligned activations");
+    const bool want_grads = BWD && gw_re != nullptr;
+    if (want_grads && (gw_im == nullptr || gb == nullptr)) return fail("gw_re, gw_im and gb must be given together");
+    if (want_grads && xlow == nullptr) return fail("filter gradients need xlow saved by sml_forward_ext");
+    const size_t part_bytes = sizeof(sml::cf) * (size_t)B * D * (size_t)p.k;
+    const size_t need_ws = part_bytes + sizeof(float) * (size_t)B * D;
+    if (want_grads && (ws == nullptr || ws_bytes < need_ws))
+        return fail("workspace too small: need %zu bytes (sml_workspace_bytes), got %zu", need_ws, ws_bytes);
+    const sml::cf* gtab = nullptr;
+    if (twiddle_table(st, T, stream, &gtab)) return 1;
+    // forward: in = x (input window), out = y (output window); backward: in = g (output window), out = gx (input window)
+    const int rows_in = BWD ? g.T_out : g.T_in, row0_in = BWD ? g.out_row0 : g.in_row0;
+    const int rows_out = BWD ? g.T_in : g.T_out, row0_out = BWD ? g.in_row0 : g.out_row0;
+    CUtensorMap map_in, map_out, map_res;
+    if (encode_act_map(&map_in, in, B, T, D, io_dtype, p, rows_in)) return 1;
+    if (encode_act_map(&map_out, out, B, T, D, io_dtype, p, rows_out)) return 1;
+    const bool res = !BWD && e && e->residual != nullptr;
+    if (res) { if (encode_act_map(&map_res, e->residual, B, T, D, io_dtype, p, rows_out)) return 1; }
+    else map_res = map_out;
+    sml::FastParams prm{};
+    prm.out = out; prm.w_re = w_re; prm.w_im = w_im; prm.bias = BWD ? nullptr : bias;
+    prm.xlow = reinterpret_cast<sml::cf*>(xlow);
+    prm.gw_re = BWD ? gw_re : nullptr;
+    prm.gpart = want_grads ? reinterpret_cast<sml::cf*>(ws) : nullptr;
+    prm.gbpart = want_grads ? reinterpret_cast<float*>(static_cast<char*>(ws) + part_bytes) : nullptr;
+    prm.gtab = gtab;
+    prm.B = B; prm.T = T; prm.D = D; prm.F = F; prm.k = p.k; prm.R = p.R;
+    prm.ntd = (D + 2 * p.P - 1) / (2 * p.P);
+    prm.ntiles = B * prm.ntd;
+    prm.invT = 1.0f / (float)T;
+    prm.dbg = debug_record();
+    prm.stats = (!BWD && e) ? reinterpret_cast<const float2*>(e->row_stats) : nullptr;
+    prm.scale = e ? e->chan_scale : nullptr;
+    prm.wnyq = e ? e->w_nyq : nullptr;
+    prm.sb_re = (!BWD && e) ? e->sb_re : nullptr;
+    prm.sb_im = (!BWD && e) ? e->sb_im : nullptr;
+    prm.sb_nyq = (!BWD && e && e->w_nyq) ? e->sb_nyq : nullptr;
+    if (prm.sb_re != nullptr && prm.sb_im == nullptr) return fail("sb_re and sb_im must be given together");
+    prm.xnyq = e ? e->x_nyq : nullptr;
+    prm.gnyqpart = (BWD && e) ? e->g_nyq : nullptr;
+    prm.res = res ? 1 : 0;
+    if (row0_out != 0) return fail("the backward of a problem with in_row0 != 0 is not supported (its output rows would start at a shifted row)");
+    prm.in_q = row0_in / p.R; prm.in_r = row0_in % p.R;
+    const int slots = st->sm_count * p.ctas_per_sm;
+    const int grid = prm.ntiles < slots ? prm.ntiles : slots;
+    if (launch_fast_ext<IO, BWD>(p, map_in, map_out, map_res, prm, grid, stream)) return 1;
+    if (want_grads && launch_filtergrad_reduce(prm.gpart, prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k, nullptr, nullptr, stream)) return 1;
+    return 0;
+}
+
+template <typename IO>
+int ln_stats_impl(const void* x, void* stats, int B, int T, int T_in, int in_row0, int D, float eps, cudaStream_t stream) {
+    const long long nrows = (long long)B * T;
+    const bool vec = ((uintptr_t)x % 16 == 0) && (D % sml::Vec16<IO>::N == 0);
+    const unsigned blocks = (unsigned)((nrows + 7) / 8);
+    if (vec) sml::ln_stats_kernel<IO, true><<<blocks, 256, 0, stream>>>((const IO*)x, (float2*)stats, nrows, T, T_in, in_row0, D, eps);
+    else sml::ln_stats_kernel<IO, false><<<blocks, 256, 0, stream>>>((const IO*)x, (float2*)stats, nrows, T, T_in, in_row0, D, eps);
+    count_launch();
+    SML_CUDA(cudaGetLastError());
+    return 0;
+}
+template <typename IO>
+int ln_backward_impl(const void* gh, const void* x, const void* stats, const void* gres, const float* cadd, void* gx, int B, int T,
+                     int T_in, int in_row0, int D, cudaStream_t stream) {
+    const long long nrows = (long long)B * T_in;
+    const bool vec = ((uintptr_t)x % 16 == 0) && ((uintptr_t)gh % 16 == 0) && ((uintptr_t)gx % 16 == 0) &&
+                     (gres == nullptr || (uintptr_t)gres % 16 == 0) && (D % sml::Vec16<IO>::N == 0);
+    const unsigned blocks = (unsigned)((nrows + 7) / 8);
+    if (vec) sml::ln_backward_kernel<IO, true><<<blocks, 256, 0, stream>>>((const IO*)gh, (const IO*)x, (const float2*)stats, (const IO*)gres, cadd, (IO*)gx, nrows, T, T_in, in_row0, D);
+    else sml::ln_backward_kernel<IO, false><<<blocks, 256, 0, stream>>>((const IO*)gh, (const IO*)x, (const float2*)stats, (const IO*)gres, cadd, (IO*)gx, nrows, T, T_in, in_row0, D);
+    count_launch();
     SML_CUDA(cudaGetLastError());
     return 0;
 }
@@ -585,7 +715,7 @@ int fwd_bwd_host_body(HostPipe& hp, const void* x, const void* g, const float* w
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int sml_abi_version(void) { return 2; }
+int sml_abi_version(void) { return 3; }
 
 const char* sml_last_error(void) { return g_err; }
 
@@ -677,6 +807,72 @@ int sml_backward_allreduce(const void* g, const void* xlow, const float* w_re, c
                                     (cudaStream_t)stream, (float*)flat_multicast, (float*)flat_next);
     return backward_impl<__nv_bfloat16>(g, xlow, w_re, w_im, gx, gw_re, gw_im, gb, workspace, workspace_bytes, B, T, D, F,
                                         io_dtype, (cudaStream_t)stream, (float*)flat_multicast, (float*)flat_next);
+}
+
+int sml_ext_supported(int B, int T, int D, int F, int io_dtype, const sml_ext* ext) {
+    if (check_common(&B, &B, B, T, D, F, io_dtype)) return 1;
+    g_err[0] = 0;
+    const Plan p = make_plan_ext(T, D, F, io_dtype);
+    ExtGeom g;
+    return ext_check(p, T, D, ext, &g);
+}
+
+int sml_forward_ext(const void* x, const float* w_re, const float* w_im, const float* bias, void* y, void* xlow_save, int B,
+                    int T, int D, int F, int io_dtype, const sml_ext* ext, void* stream) {
+    if (check_common(x, y, B, T, D, F, io_dtype)) return 1;
+    if (w_re == nullptr || w_im == nullptr) return fail("null filter pointer");
+    g_err[0] = 0;
+    if (io_dtype == SML_DTYPE_F32)
+        return ext_impl<float, false>(x, w_re, w_im, bias, y, xlow_save, nullptr, nullptr, nullptr, nullptr, 0, B, T, D, F, io_dtype, ext,
+                                      (cudaStream_t)stream);
+    return ext_impl<__nv_bfloat16, false>(x, w_re, w_im, bias, y, xlow_save, nullptr, nullptr, nullptr, nullptr, 0, B, T, D, F, io_dtype,
+                                          ext, (cudaStream_t)stream);
+}
+
+int sml_backward_ext(const void* g, const void* xlow, const float* w_re, const float* w_im, void* gx, float* gw_re, float* gw_im,
+                     float* gb, void* workspace, size_t workspace_bytes, int B, int T, int D, int F, int io_dtype,
+                     const sml_ext* ext, void* stream) {
+    if (check_common(g, gx, B, T, D, F, io_dtype)) return 1;
+    if (w_re == nullptr || w_im == nullptr) return fail("null filter pointer");
+    g_err[0] = 0;
+    if (io_dtype == SML_DTYPE_F32)
+        return ext_impl<float, true>(g, w_re, w_im, nullptr, gx, const_cast<void*>(xlow), gw_re, gw_im, gb, workspace, workspace_bytes, B,
+                                     T, D, F, io_dtype, ext, (cudaStream_t)stream);
+    return ext_impl<__nv_bfloat16, true>(g, w_re, w_im, nullptr, gx, const_cast<void*>(xlow), gw_re, gw_im, gb, workspace,
+                                         workspace_bytes, B, T, D, F, io_dtype, ext, (cudaStream_t)stream);
+}
+
+int sml_ln_stats(const void* x, void* stats, int B, int T, int T_in, int in_row0, int D, float eps, int io_dtype, void* stream) {
+    if (x == nullptr || stats == nullptr) return fail("null pointer");
+    if (B < 1 || T < 1 || D < 1 || T_in < 1 || in_row0 < 0 || in_row0 + T_in > T) return fail("invalid shape B=%d T=%d T_in=%d in_row0=%d D=%d", B, T, T_in, in_row0, D);
+    if (io_dtype != SML_DTYPE_F32 && io_dtype != SML_DTYPE_BF16) return fail("unsupported io_dtype %d", io_dtype);
+    g_err[0] = 0;
+    if (io_dtype == SML_DTYPE_F32) return ln_stats_impl<float>(x, stats, B, T, T_in, in_row0, D, eps, (cudaStream_t)stream);
+    return ln_stats_impl<__nv_bfloat16>(x, stats, B, T, T_in, in_row0, D, eps, (cudaStream_t)stream);
+}
+
+int sml_ln_backward(const void* gh, const void* x, const void* stats, const void* g_res, const float* chan_add, void* gx, int B,
+                    int T, int T_in, int in_row0, int D, int io_dtype, void* stream) {
+    if (gh == nullptr || x == nullptr || stats == nullptr || gx == nullptr) return fail("null pointer");
+    if (B < 1 || T < 1 || D < 1 || T_in < 1 || in_row0 < 0 || in_row0 + T_in > T) return fail("invalid shape B=%d T=%d T_in=%d in_row0=%d D=%d", B, T, T_in, in_row0, D);
+    if (io_dtype != SML_DTYPE_F32 && io_dtype != SML_DTYPE_BF16) return fail("unsupported io_dtype %d", io_dtype);
+    g_err[0] = 0;
+    if (io_dtype == SML_DTYPE_F32) return ln_backward_impl<float>(gh, x, stats, g_res, chan_add, gx, B, T, T_in, in_row0, D, (cudaStream_t)stream);
+    return ln_backward_impl<__nv_bfloat16>(gh, x, stats, g_res, chan_add, gx, B, T, T_in, in_row0, D, (cudaStream_t)stream);
+}
+
+int sml_spectral_ema_scan(const void* chunks, const void* state_in, const float* rho, const float* theta, void* state_out, int B,
+                          int S, int F, int mode, void* stream) {
+    if (chunks == nullptr || rho == nullptr || theta == nullptr || state_out == nullptr) return fail("null pointer");
+    if (B < 1 || S < 0 || F < 1) return fail("invalid shape B=%d S=%d F=%d", B, S, F);
+    if (mode != 0 && mode != 1) return fail("unknown SpectralEMA mode %d (0 = aligned, 1 = polar)", mode);
+    g_err[0] = 0;
+    const long long n = (long long)B * F;
+    sml::spectral_ema_scan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float2*)chunks, (const float2*)state_in, rho, theta, (float2*)state_out, B, S, F, mode);
+    count_launch();
+    SML_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int sml_fwd_bwd_host(const void* x, const void* g, const float* w_re, const float* w_im, const float* bias, void* y,

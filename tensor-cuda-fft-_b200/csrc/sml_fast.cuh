@@ -52,6 +52,18 @@ struct FastParams {
     int ntiles;            // B * ntd
     float invT;
     unsigned int* dbg;     // host-mapped debug record (null unless SML_DEBUG is set): filled by a timed-out mbarrier wait
+    // ---- extended kernels (template flag EXT) only: the hosting block's prologue / epilogue fused around the transform ----
+    const float2* stats;   // (B, T) {mean, rstd} per TRANSFORM row ({0,0} on zero-padding rows): LayerNorm on load, or null
+    const float* scale;    // (B, D) per (batch element, channel) factor on the filtered spectrum (context gate), or null
+    const float* sb_re;    // (D, F) "spectral bias": added to the filtered spectrum X W before the channel factor (FWD only) --
+    const float* sb_im;    //        the image of a LayerNorm beta on a zero-padded window (beta * rfft(rect) * W0), or null
+    const float* sb_nyq;   // (D,) its bin T/2, or null
+    const float* wnyq;     // (D,) real weight of the bin T/2 (full half-spectrum filters, irfft semantics), or null
+    float* xnyq;           // (B, D) spectrum at the bin T/2 (real): written by FWD, read by BWD
+    float* gnyqpart;       // (B, D) per-batch-element gradient terms of wnyq, written by BWD
+    int res;               // 1: tmap_res describes a residual tensor (output geometry) that is added to the output rows
+    int in_q, in_r;        // input row i is transform row in_row0 + i, in_row0 = R * in_q + in_r (rows outside the input read as
+                           // zero); output row i is transform row i (rows past the output tensor are not written)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -237,12 +249,23 @@ __device__ __forceinline__ void prefetch_xlow_l2(const FastParams& prm, int b, i
 // filter gradient terms G conj(X) (reference wirtinger_ops.py:77-80), one per batch element (summed by
 // filtergrad_reduce_kernel).
 // ------------------------------------------------------------------------------------------------
-template <int NR, int KJ, bool BWD>
+template <int NR, int KJ, bool BWD, bool EXT = false>
 __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const FastParams& prm, int b, int d0, int ff1, int lane) {
     constexpr int NJ = 2 * KJ;
     const int D = prm.D;
     const bool pvalid = d0 < D;
     const bool grads = BWD && prm.gw_re != nullptr;
+    // EXT: per-(batch element, channel) factor on the filtered spectrum, and the raw analysis value of the bin -T/2
+    float sc0 = 1.f, sc1 = 1.f;
+    cf znyq = cf{0.f, 0.f};
+    if constexpr (EXT) {
+        if (prm.scale != nullptr && pvalid) {
+            sc0 = __ldg(prm.scale + (size_t)b * D + d0);
+            sc1 = __ldg(prm.scale + (size_t)b * D + d0 + 1);
+        }
+        // the bin -T/2 = -NR*KJ sits at index KJ of the f1 = 0 lanes (the host only offers wnyq on plans with NR*KJ = T/2)
+        if (prm.wnyq != nullptr) znyq = acc[KJ];
+    }
     // the bin -fs of (ff1, j) lives in lane NR - ff1 of the same warp at index NJ - 1 - j (ff1 = 0: own index NJ - j)
     const int src_lane = (lane & ~(NR - 1)) | ((NR - ff1) & (NR - 1));
     const size_t wrow0 = (size_t)d0 * prm.F, wrow1 = wrow0 + prm.F;
@@ -288,9 +311,14 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
             self_mirror = acc[NJ - 1 - j];   // = acc[NJ - (j + 1)], read before this iteration overwrites it
             const cf zp = acc[j], zm = cf{mre, mim};
             // Hermitian split: spectra of the two real channels at +af
-            const cf s0 = cf{0.5f * (zp.re + zm.re), 0.5f * (zp.im - zm.im)};
-            const cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
+            cf s0 = cf{0.5f * (zp.re + zm.re), 0.5f * (zp.im - zm.im)};
+            cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
             const cf w0 = cf{wv[jj][0], wv[jj][1]}, w1 = cf{wv[jj][2], wv[jj][3]};
+            const float gdc0 = s0.re, gdc1 = s1.re;   // BWD: sum_t g of the two channels when af == 0 (before any scaling)
+            if constexpr (EXT && BWD) {   // y = scale * ifft(W X): the gradient entering the filter is scale * G
+                s0 = cf{s0.re * sc0, s0.im * sc0};
+                s1 = cf{s1.re * sc1, s1.im * sc1};
+            }
             cf a0, a1;
             if constexpr (!BWD) {
                 if (live && prm.xlow != nullptr) {
@@ -299,6 +327,14 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
                 }
                 a0 = cmul(s0, w0);
                 a1 = cmul(s1, w1);
+                if constexpr (EXT) {
+                    if (prm.sb_re != nullptr && live) {
+                        a0 = cf{a0.re + __ldg(prm.sb_re + wrow0 + af), a0.im + __ldg(prm.sb_im + wrow0 + af)};
+                        a1 = cf{a1.re + __ldg(prm.sb_re + wrow1 + af), a1.im + __ldg(prm.sb_im + wrow1 + af)};
+                    }
+                    a0 = cf{a0.re * sc0, a0.im * sc0};
+                    a1 = cf{a1.re * sc1, a1.im * sc1};
+                }
             } else {
                 if (live && grads) {
                     const cf g0 = cmulc(s0, cf{xv[jj][0].x, xv[jj][0].y});   // G conj(X)
@@ -308,8 +344,8 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
                     reinterpret_cast<float2*>(prm.gpart)[xrow0 + af] = make_float2(g0.re * prm.invT, g0.im * prm.invT);
                     reinterpret_cast<float2*>(prm.gpart)[xrow1 + af] = make_float2(g1.re * prm.invT, g1.im * prm.invT);
                     if (af == 0) {
-                        prm.gbpart[(size_t)b * D + d0] = s0.re;
-                        prm.gbpart[(size_t)b * D + d0 + 1] = s1.re;
+                        prm.gbpart[(size_t)b * D + d0] = gdc0;
+                        prm.gbpart[(size_t)b * D + d0 + 1] = gdc1;
                     }
                 }
                 a0 = cmulc(s0, w0);   // G conj(W)
@@ -337,6 +373,30 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
         for (int idx = NJ - 1; idx > KJ; --idx) acc[idx] = acc[idx - 1];
         acc[KJ] = cf{0.f, 0.f};
     }
+    if constexpr (EXT) {
+        // bin T/2 (== -T/2): Z = X_d + i X_{d+1} with both spectra real there; irfft semantics: weight 1/T, real filter weight
+        if (prm.wnyq != nullptr && ff1 == 0) {
+            cf c = cf{0.f, 0.f};
+            if (pvalid) {
+                const float wn0 = __ldg(prm.wnyq + d0), wn1 = __ldg(prm.wnyq + d0 + 1);
+                const size_t o = (size_t)b * D + d0;
+                if constexpr (!BWD) {
+                    if (prm.xnyq != nullptr) { prm.xnyq[o] = znyq.re; prm.xnyq[o + 1] = znyq.im; }
+                    float b0 = 0.f, b1 = 0.f;
+                    if (prm.sb_nyq != nullptr) { b0 = __ldg(prm.sb_nyq + d0); b1 = __ldg(prm.sb_nyq + d0 + 1); }
+                    c = cf{(znyq.re * wn0 + b0) * sc0 * prm.invT, (znyq.im * wn1 + b1) * sc1 * prm.invT};
+                } else {
+                    const float g0 = znyq.re * sc0, g1 = znyq.im * sc1;
+                    if (prm.gnyqpart != nullptr && prm.xnyq != nullptr) {
+                        prm.gnyqpart[o] = g0 * prm.xnyq[o] * prm.invT;
+                        prm.gnyqpart[o + 1] = g1 * prm.xnyq[o + 1] * prm.invT;
+                    }
+                    c = cf{g0 * wn0 * prm.invT, g1 * wn1 * prm.invT};
+                }
+            }
+            acc[KJ] = c;
+        }
+    }
 }
 
 // band column j -> sub-bin column f2 (the signed column index f2s = j or j - NJ, wrapped into [0, NR))
@@ -363,10 +423,22 @@ __host__ __device__ constexpr bool band_first(int j) {
 // (A per-thread cp.async.cg load path was measured too: 0.157 vs 0.183 ms in a copy-only stream of 32-byte rows,
 //  tools/microbench/ldst_stream.cu, but 0.227 vs 0.198 ms inside this kernel, where the copies compete with the exchange
 //  traffic for the LSU / shared-memory pipe -- TMA stays the load path.)
-template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, int XB>
+// EXT = true: the same kernel with the hosting block's prologue / epilogue fused in (all optional at run time, FastParams):
+//   * LayerNorm on load: x^ = (x - mean[t]) * rstd[t] from a per-row statistics array (the affine part folds into the filter
+//     and the bias on the host: gamma scales the filter rows, beta is a DC term);
+//   * residual add on store: the staging tile first receives the residual rows of the pass by TMA (prm.res, tmap_res: the
+//     tile is idle between two stores), the second-stage outputs are added in place;
+//   * input / output row windows (in_row0 and the row counts of the tensor maps): rows outside the input are zero-filled
+//     by TMA, rows past the output are clipped by TMA -- zero-padded ("linear") convolution and overlap-save without a
+//     padded copy (an output window that starts at row o > 0 is a phase ramp exp(2 pi i f o / T) on the filter: host side);
+//   * a per-(batch element, channel) factor on the filtered spectrum and a real weight for the bin T/2 (irfft semantics of a
+//     full half-spectrum multiplier) -- the causal FFT-convolution core of fft_lm's FixedSpectralBlock.
+// With a residual the load stream of a work item is R analysis loads followed by R residual loads, all through the same XB
+// landing tiles and mbarriers (load n -> tile n % XB).
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, int XB, bool EXT = false>
 __global__ void __launch_bounds__(NR* P, MINB)
     sml_fast_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
-                    const FastParams prm) {
+                    const __grid_constant__ CUtensorMap tmap_res, const FastParams prm) {
     using C = FastCfg<NR, P, IO, XB>;
     static_assert(XB == 1 || XB == 2, "one or two landing tiles");
     constexpr int NT = C::NT, XS = C::XS;
@@ -399,19 +471,35 @@ __global__ void __launch_bounds__(NR* P, MINB)
     const float2* const gtab = reinterpret_cast<const float2*>(prm.gtab);
 
     const int my_ntiles = (prm.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total_loads = my_ntiles * R;
+    const bool res = EXT && prm.res != 0;        // residual rows ride through the landing tiles during synthesis
+    const int lpi = res ? 2 * R : R;             // loads per work item
+    const int total_loads = my_ntiles * lpi;
 
-    auto issue_load = [&](int L) {   // thread 0 only.  load L = (tile L / R, pass L % R) -> X
+    // rows of pass r in a tensor whose row i is transform row row0 + i (row0 = R*q0 + r0): t - row0 = R*(m - q0 - borrow) + rs
+    auto shifted = [&](int r, int q0, int r0, int& rs, int& mshift) {
+        rs = r - r0;
+        mshift = q0;
+        if (rs < 0) { rs += R; mshift += 1; }
+    };
+    auto issue_load = [&](int L) {   // thread 0 only.  load L = (work item L / lpi, pass) -> X; passes >= R fetch the residual rows
         if (L >= total_loads) return;
-        const int it = L / R, r = L - it * R;
+        const int it = L / lpi;
+        int r = L - it * lpi;
+        const bool resload = r >= R;
+        if (resload) r -= R;
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         const int b = tile / prm.ntd, dt = tile - b * prm.ntd;
+        int rs = r, mshift = 0;
+        if constexpr (EXT) { if (!resload) shifted(r, prm.in_q, prm.in_r, rs, mshift); }   // residual rows: output geometry, no shift
+        const CUtensorMap* const tm = (EXT && resload) ? &tmap_res : &tmap_in;
         fence_proxy_async();
         mbar_expect_tx(mbar + xslot(L), C::LOAD_BYTES);
 #pragma unroll
         for (int bx = 0; bx < C::NBOX; ++bx)
-            tma_load_4d(xbuf(L) + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), &tmap_in, mbar + xslot(L), dt * 2 * P, r, bx * C::BOXROWS, b);
+            tma_load_4d(xbuf(L) + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), tm, mbar + xslot(L), dt * 2 * P, rs, bx * C::BOXROWS - mshift, b);
     };
+    // (stores are never shifted: TMA tensor stores fault on negative coordinates -- measured -- so an output window that
+    //  does not start at transform row 0 is expressed as a phase ramp on the filter by the host instead)
     auto issue_store = [&](const unsigned char* stage, int b, int dt, int r) {   // thread 0 only: staging tile -> rows r + R*m
 #pragma unroll
         for (int bx = 0; bx < C::NBOX; ++bx)
@@ -467,16 +555,37 @@ __global__ void __launch_bounds__(NR* P, MINB)
                 cjv = cj_load(r);
                 if (r + 1 == R) cjn = cj_load(0);   // first synthesis pass
             }
-            mbar_wait(mbar + xslot(L), xparity(L), prm.dbg, 1u, (uint32_t)L);
             cf v[NR];
-            {
+            bool ln_done = false;
+            if constexpr (EXT) {
+                if (prm.stats != nullptr) {
+                    // LayerNorm on load: the row statistics of this pass are fetched before the tile wait (L2 hits: the 96
+                    // channel tiles of a batch element share them), x^ = (x - mean) * rstd as one FMA per element
+                    float2 st[NR];
+                    const float2* sp = prm.stats + (size_t)b * T + (size_t)R * tm2 + r;
+#pragma unroll
+                    for (int m1 = 0; m1 < NR; ++m1) st[m1] = __ldg(sp + (size_t)m1 * NR * R);
+                    mbar_wait(mbar + xslot(L), xparity(L), prm.dbg, 1u, (uint32_t)L);
+                    const IO* src = reinterpret_cast<const IO*>(xbuf(L)) + tm2 * 2 * P + 2 * tp;
+#pragma unroll
+                    for (int m1 = 0; m1 < NR; ++m1) {
+                        const cf x = PairIO<IO>::load_s(src + m1 * NR * 2 * P);
+                        const float a = st[m1].y, c = -st[m1].x * st[m1].y;
+                        v[m1] = cf{fmaf(x.re, a, c), fmaf(x.im, a, c)};
+                    }
+                    ln_done = true;
+                }
+            }
+            if (!ln_done) {
+                mbar_wait(mbar + xslot(L), xparity(L), prm.dbg, 1u, (uint32_t)L);
                 const IO* src = reinterpret_cast<const IO*>(xbuf(L)) + tm2 * 2 * P + 2 * tp;
 #pragma unroll
                 for (int m1 = 0; m1 < NR; ++m1) v[m1] = PairIO<IO>::load_s(src + m1 * NR * 2 * P);
             }
             // the last warp to drain the tile re-arms it right away with the next load that lands there (XB ahead).  The tile
-            // of a work item's last pass becomes the store staging buffer instead and is re-armed after the last store.
-            if (r + 1 < R) {
+            // of a work item's last pass becomes the store staging buffer instead and is re-armed after the last store
+            // (with a residual and two tiles it takes a residual load right away: staging alternates between the tiles).
+            if (r + 1 < R || (res && XB == 2)) {
                 __syncwarp();
                 if ((tid & 31) == 0) {
                     __threadfence_block();
@@ -512,11 +621,13 @@ __global__ void __launch_bounds__(NR* P, MINB)
         }
 
         // ===================== mid phase: un-mix the channel pair, filter, re-pack =====================
-        spectral_mid_phase<NR, KJ, BWD>(acc, prm, b, dt * 2 * P + 2 * fp2, ff1, tid & 31);
+        spectral_mid_phase<NR, KJ, BWD, EXT>(acc, prm, b, dt * 2 * P + 2 * fp2, ff1, tid & 31);
 
         // ===================== synthesis: transpose of analysis; rows leave through a TMA store from X =====================
-        unsigned char* const stage = xbuf(L - 1);   // tile of this work item's last load, drained by every warp (barrier (A'))
+        // staging tile: the tile of this work item's last load, drained by every warp (barrier (A')); with a residual the
+        // tile that received (or is about to receive) the residual rows of the pass: load L
         for (int r = 0; r < R; ++r) {
+            unsigned char* const stage = res ? xbuf(L) : xbuf(L - 1);
             // twiddle seeds: v[m2] *= conj(W_T^{r f1} * (W_T^{R f1})^{m2})
             const float2 sr = __ldg(gtab + r * ff1);
             const float2 beta = __ldg(gtab + R * ff1);
@@ -544,7 +655,15 @@ __global__ void __launch_bounds__(NR* P, MINB)
                 for (int m2 = 0; m2 < NR; ++m2) xb[m2 * P * XS] = v[m2];
             }
             if (tid < NJ && r + 1 < R) cj[(slot ^ 1) * CJN + tid] = cf{cjn.x, cjn.y};
-            if (tid == 0 && r > 0) tma_store_wait_read();   // X may be overwritten after (B')
+            if (tid == 0) {
+                if (r > 0) tma_store_wait_read();   // X may be overwritten after (B')
+                if (res) {
+                    // one tile: fetch this pass's residual rows now (the tile is free: drained / its last store has been read);
+                    // two tiles: the tile of pass r - 1 is free, it takes the residual rows of pass r + 1
+                    if (XB == 1) issue_load(L);
+                    else if (r > 0) issue_load(L + 1);
+                }
+            }
             __syncthreads();   // (B')
             {
                 const float4* xrow = reinterpret_cast<const float4*>(ybuf + tid * XS);
@@ -556,7 +675,13 @@ __global__ void __launch_bounds__(NR* P, MINB)
                 }
             }
             Dft<NR, +1>::run(v);   // over f1 -> m1
-            {
+            if (res) {
+                mbar_wait(mbar + xslot(L), xparity(L), prm.dbg, 2u, (uint32_t)L);   // residual rows of this pass have landed
+                IO* dst = reinterpret_cast<IO*>(stage) + tm2 * 2 * P + 2 * tp;
+#pragma unroll
+                for (int m1 = 0; m1 < NR; ++m1) PairIO<IO>::store_s(dst + m1 * NR * 2 * P, cadd(v[m1], PairIO<IO>::load_s(dst + m1 * NR * 2 * P)));
+                ++L;
+            } else {
                 IO* dst = reinterpret_cast<IO*>(stage) + tm2 * 2 * P + 2 * tp;
 #pragma unroll
                 for (int m1 = 0; m1 < NR; ++m1) PairIO<IO>::store_s(dst + m1 * NR * 2 * P, v[m1]);

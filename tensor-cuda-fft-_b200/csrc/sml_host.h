@@ -77,5 +77,9 @@ void count_launch(int n = 1);
 template <typename IO, bool BWD>
 int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
                 cudaStream_t stream);
+// the extended kernels (block prologue / epilogue fused in), instantiated in sml_inst_ext_*.cu
+template <typename IO, bool BWD>
+int launch_fast_ext(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const CUtensorMap& map_res,
+                    const sml::FastParams& prm, int grid, cudaStream_t stream);
 
 }   // namespace sml_host

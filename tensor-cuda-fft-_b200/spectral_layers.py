@@ -164,6 +164,120 @@ class _SpectralMixFn(torch.autograd.Function):
                 None)
 
 
+_EXT_CACHE = {}
+
+
+def _ext_supported(B: int, T: int, D: int, Fn: int, io: int, T_in: int = 0, T_out: int = 0, nyq: bool = False) -> bool:
+    """True if the extended fused kernels (sml_forward_ext) take this problem; cached per shape."""
+    key = (B, T, D, Fn, io, T_in, T_out, nyq)
+    ok = _EXT_CACHE.get(key)
+    if ok is None:
+        import ctypes
+        ext = _native.make_ext(T_in=T_in, T_out=T_out)
+        if nyq:
+            ext.w_nyq = 1      # only tested for NULL by sml_ext_supported
+        ok = _native.lib().sml_ext_supported(B, T, D, Fn, io, ctypes.byref(ext)) == 0
+        if len(_EXT_CACHE) < 4096:
+            _EXT_CACHE[key] = ok
+    return ok
+
+
+class _LNSpectralResidualFn(torch.autograd.Function):
+    """``x + spectral_mix(LayerNorm(x))`` -- the way SpectralMLPBlock calls the layer (spectral_layers.py:161, :185) -- as
+    three launches instead of seven HBM passes: a row-statistics pre-pass (sml_ln_stats), ONE fused kernel that normalises the
+    rows while it loads them and adds the residual rows while it stores (sml_forward_ext), and in the backward the fused
+    kernel (sml_backward) followed by one LayerNorm-backward + skip-connection kernel (sml_ln_backward).
+
+    The LayerNorm affine part never reaches the kernel: the layer is linear in its input, so gamma scales the filter rows and
+    beta is a DC term, ``w_eff = gamma[:, None] * W``, ``bias_eff = bias + beta * W_re[:, 0]`` -- computed by the caller with
+    ordinary autograd ops, so the gradients of gamma / beta / W / bias follow from the gradients returned here."""
+
+    @staticmethod
+    def forward(ctx, x, w_re, w_im, bias, eps):
+        import ctypes
+        B, T, D = x.shape
+        Fn = w_re.shape[1]
+        io = _IO_DTYPES[x.dtype]
+        lib = _native.lib()
+        xc = x.contiguous()
+        if xc.data_ptr() % 16:
+            xc = xc.clone()
+        wr, wi, bs = _f32c(w_re), _f32c(w_im), _f32c(bias)
+        stats = torch.empty(B, T, 2, dtype=torch.float32, device=x.device)
+        y = torch.empty_like(xc)
+        need_filter_grad = any(ctx.needs_input_grad[1:4])
+        xlow = None
+        if need_filter_grad:
+            xlow = torch.empty(max(_shape_info(B, T, D, Fn, io)[1] // 8, 1), dtype=torch.complex64, device=x.device)
+        ext = _native.make_ext(row_stats=stats, residual=xc)
+        with _on_device(x.device):
+            st = _stream_handle(x.device)
+            _native.check(lib.sml_ln_stats(_ptr(xc), _ptr(stats), B, T, T, 0, D, float(eps), io, st))
+            _native.check(lib.sml_forward_ext(_ptr(xc), _ptr(wr), _ptr(wi), _ptr(bs), _ptr(y), _ptr(xlow), B, T, D, Fn, io,
+                                              ctypes.byref(ext), st))
+        ctx.save_for_backward(xc, stats, wr, wi, xlow)
+        ctx.shape = (B, T, D, Fn, io)
+        ctx.param_dtypes = (w_re.dtype, w_im.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        xc, stats, wr, wi, xlow = ctx.saved_tensors
+        B, T, D, Fn, io = ctx.shape
+        lib = _native.lib()
+        gc = g.contiguous()
+        if gc.dtype != xc.dtype:
+            gc = gc.to(xc.dtype)
+        if gc.data_ptr() % 16:
+            gc = gc.clone()
+        gh = torch.empty_like(gc)      # dL/dx^ (gradient with respect to the normalised rows)
+        want = xlow is not None
+        gwr = gwi = gb = ws = None
+        ws_bytes = 0
+        if want:
+            flat = torch.empty(2 * D * Fn + D, dtype=torch.float32, device=gc.device)
+            gwr, gwi, gb = flat[: D * Fn].view(D, Fn), flat[D * Fn: 2 * D * Fn].view(D, Fn), flat[2 * D * Fn:]
+            ws_bytes = _shape_info(B, T, D, Fn, io)[2]
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gc.device)
+        gx = torch.empty_like(gc)
+        with _on_device(gc.device):
+            st = _stream_handle(gc.device)
+            _native.check(lib.sml_backward(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gh), _ptr(gwr), _ptr(gwi), _ptr(gb),
+                                           _ptr(ws), ws_bytes, B, T, D, Fn, io, st))
+            _native.check(lib.sml_ln_backward(_ptr(gh), _ptr(xc), _ptr(stats), _ptr(gc), None, _ptr(gx), B, T, T, 0, D, io, st))
+        need = ctx.needs_input_grad
+        dt = ctx.param_dtypes
+        return (gx if need[0] else None,
+                gwr.to(dt[0]) if (want and need[1]) else None,
+                gwi.to(dt[1]) if (want and need[2]) else None,
+                gb.to(dt[2]) if (want and need[3]) else None,
+                None)
+
+
+def ln_spectral_mix_residual(x: torch.Tensor, norm: nn.LayerNorm, layer: "SpectralMixingLayer") -> torch.Tensor:
+    """``x + layer(norm(x))`` through the fused LayerNorm-on-load / residual-on-store kernel; raises if the shape is not
+    one the extended kernels take (callers test ``fused_block_supported`` first)."""
+    gamma = norm.weight if norm.weight is not None else torch.ones(x.shape[-1], device=x.device)
+    w_re = gamma.float()[:, None] * layer.weight_real.float()
+    w_im = gamma.float()[:, None] * layer.weight_imag.float()
+    bias = layer.bias.float()
+    if norm.bias is not None:
+        bias = bias + norm.bias.float() * layer.weight_real.float()[:, 0]
+    return _LNSpectralResidualFn.apply(x, w_re, w_im, bias, norm.eps)
+
+
+def fused_block_supported(x: torch.Tensor, norm: nn.LayerNorm, layer: "SpectralMixingLayer") -> bool:
+    if not (x.is_cuda and x.dim() == 3 and x.dtype in _IO_DTYPES and x.numel() > 0):
+        return False
+    if not (layer.learnable and layer.weight_real is not None) or tuple(norm.normalized_shape) != (x.shape[-1],):
+        return False
+    if layer.training and layer.dropout.p > 0.0:      # dropout sits between the layer and the skip connection (:118, :185)
+        return False
+    B, T, D = x.shape
+    return _ext_supported(B, T, D, layer.weight_real.shape[1], _IO_DTYPES[x.dtype])
+
+
 def spectral_mix(x: torch.Tensor, weight_real: torch.Tensor, weight_imag: torch.Tensor,
                  bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Functional form of the fused layer (no dropout)."""
@@ -285,9 +399,15 @@ class SpectralMLPBlock(nn.Module):
             nn.Linear(hidden_dim, embed_dim),
             nn.Dropout(dropout),
         )
+        self.fuse_norm_residual = True      # not a parameter / buffer: the reference's state_dict loads unchanged
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = x + self.spectral_mix(self.norm1(x))
+        # spectral half: one fused kernel (LayerNorm on load, residual on store) where the extended kernels take the
+        # shape and dropout is inactive; otherwise the reference's composition around the fused layer
+        if self.fuse_norm_residual and fused_block_supported(x, self.norm1, self.spectral_mix):
+            x = ln_spectral_mix_residual(x, self.norm1, self.spectral_mix)
+        else:
+            x = x + self.spectral_mix(self.norm1(x))
         x = x + self.mlp(self.norm2(x))
         return x
 

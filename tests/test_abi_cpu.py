@@ -27,7 +27,7 @@ def test_header_symbols_exported(native):
     raw = ctypes.CDLL(native.LIB_PATH)
     for name in sorted(declared):
         assert hasattr(raw, name), f"{name} declared in the header but not exported"
-    assert native.lib().sml_abi_version() == 2
+    assert native.lib().sml_abi_version() == 3
 
 
 def test_plan_selection(native):
