@@ -99,6 +99,7 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=0, help="CPU legs: batch of the timed sample (0 = reference arm: the full batch; cpu_baseline leg: 2)")
     ap.add_argument("--config", choices=["cfg1", "cfg2", "cfg3", "cfg5"], default="cfg2")
     ap.add_argument("--no-bf16", action="store_true", help="skip the bf16 I/O sub-record of the default line")
+    ap.add_argument("--no-blocks", action="store_true", help="skip the block-level (f-1 / f-2) sub-record of the default line")
     args = ap.parse_args()
     args.scaling = "weak"
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -527,6 +528,14 @@ def run_ours(args):
         except Exception as e:
             graphed = {"unavailable": str(e).splitlines()[0][:200]}
 
+    # ---- block rows: the layer inside its callers, fused prologue / epilogue vs the unfused composition ----
+    blocks = None
+    if world == 1 and args.config == "cfg2" and args.dtype == "f32" and not args.no_blocks:
+        try:
+            blocks = run_blocks(prob, B, T, D, roof, barrier)
+        except Exception as e:
+            blocks = {"unavailable": str(e).splitlines()[0][:200]}
+
     # ---- end to end: the reference-facing C-ABI call with HOST buffers (sml_fwd_bwd_host): pinned host x, g in;
     #      y, gx and the filter/bias gradients back in host memory; all copies inside the timed region ----
     e2e = None
@@ -567,12 +576,62 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_step": roofline_step,
-            "bf16": bf16, "graphed": graphed,
+            "bf16": bf16, "graphed": graphed, "blocks": blocks,
             "e2e": e2e, "cpu_baseline": cpu, "reference_algorithm_on_gpu": gpu_ref,
         }
         print_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_blocks(prob, B, T, D, roof, barrier):
+    """Block-level rows of the default line: SpectralMLPBlock's spectral half `x + spectral_mix(norm1(x))` (spectral_layers.py:185)
+    fused (LayerNorm on load, residual on store: sml_ln_stats + sml_forward_ext, sml_backward + sml_ln_backward) against the unfused
+    composition around the same fused layer; FixedSpectralBlock's spectral half (train_fixed_full.py:498-555) at the reference's
+    default sizes.  Floor = 5 passes over the activation (x, y | g, x, gx)."""
+    import tensor_cuda_fft_b200 as pkg
+    from tensor_cuda_fft_b200 import spectral_conv as sc
+    from tensor_cuda_fft_b200 import spectral_layers as sl
+    dev = prob.x.device
+    norm = torch.nn.LayerNorm(D).to(dev)
+    layer = prob.layer
+    params = list(norm.parameters()) + list(layer.parameters())
+
+    def step(fused):
+        def run():
+            for p in params:
+                p.grad = None
+            xr = prob.x.detach().requires_grad_(True)
+            y = sl.ln_spectral_mix_residual(xr, norm, layer) if fused else xr + layer(norm(xr))
+            y.backward(prob.g)
+        return run
+
+    out = {}
+    act = B * T * D * prob.esz
+    for name, fused in (("fused", True), ("unfused", False)):
+        ms = time_steps(step(fused), 30, 5, barrier)
+        out["mlp_block_half_" + name] = {"ms_per_step": ms, "value": B * T / (ms * 1e-3), "unit": UNIT, "roofline_5pass": roof(5 * act, ms)}
+    for p in params:
+        p.grad = None
+    Bc, Tc, C, K = 64, 1024, 512, 128
+    blk = sc.FixedSpectralBlock(C, seq_len=Tc, kernel_len=K, transition_bins=16, dropout=0.0).to(dev).eval()
+    with torch.no_grad():
+        blk.kernel.normal_(std=0.1)
+    x2 = torch.randn(Bc, Tc, C, device=dev)
+    g2 = torch.randn(Bc, Tc, C, device=dev)
+
+    def conv_step():
+        for p in blk.parameters():
+            p.grad = None
+        xr = x2.detach().requires_grad_(True)
+        blk.spectral_half(xr).backward(g2)
+
+    ms = time_steps(conv_step, 30, 5, barrier)
+    out["fixed_block_half"] = {"shape": [Bc, Tc, C], "kernel_len": K, "n_fft": sc.conv_fft_len(Tc, K), "ms_per_step": ms,
+                               "value": Bc * Tc / (ms * 1e-3), "unit": UNIT, "roofline_5pass": roof(5 * Bc * Tc * C * 4, ms)}
+    out["what"] = ("mlp_block_half: x + spectral_mix(LayerNorm(x)) fwd+bwd at the headline shape, fused prologue/epilogue vs torch LayerNorm + fused "
+                   "layer + add; fixed_block_half: pre-LN causal FFT convolution + gates + residual of fft_lm's FixedSpectralBlock, fwd+bwd")
+    return out
 
 
 def _tc_default():

@@ -8,6 +8,7 @@ from .spectral_layers import (HybridSpectralAttention, SpectralMLPBlock, Spectra
 from .wirtinger_ops import (ComplexParameter, WirtingerGradient, WirtingerSpectralFilter)
 from .byte_spectral_model import ByteSpectralEmbedding, SpectralLanguageModel
 from .distributed import allreduce_filter_grads, attach_symmetric_grad_buffers, shard_batch
+from .spectral_conv import EMAConfig, FixedSpectralBlock, SpectralEMA, overlap_save_block_update
 
 __version__ = "0.1.0"
 __all__ = [
@@ -15,4 +16,5 @@ __all__ = [
     "WirtingerGradient", "ComplexParameter", "WirtingerSpectralFilter",
     "ByteSpectralEmbedding", "SpectralLanguageModel",
     "allreduce_filter_grads", "attach_symmetric_grad_buffers", "shard_batch",
+    "FixedSpectralBlock", "overlap_save_block_update", "EMAConfig", "SpectralEMA",
 ]
