@@ -44,6 +44,7 @@ const Knobs& knobs() {
         if (const char* e = getenv("SML_FAST_XB")) v.fast_xb = atoi(e);
         if (const char* e = getenv("SML_TC")) v.tc = atoi(e) != 0 ? 1 : 0;
         if (const char* e = getenv("SML_PDL")) v.pdl = atoi(e) != 0 ? 1 : 0;
+        if (const char* e = getenv("SML_EXT_CTAS")) v.ext_ctas = atoi(e);
         return v;
     }();
     return k;
@@ -397,6 +398,7 @@ Plan make_plan_ext(int T, int D, int F, int io_dtype) {
     p.tc = false;
     if (p.NR == 32) p.ctas_per_sm = 2;
     p.xb = 2;
+    if (p.NR == 32 && p.KJ <= 12 && knobs().ext_ctas == 3) { p.ctas_per_sm = 3; p.xb = 1; }   // tuning knob SML_EXT_CTAS
     if (knobs().fast_xb) p.xb = knobs().fast_xb == 2 ? 2 : 1;
     return p;
 }
@@ -916,9 +918,12 @@ int sml_wirtinger_mul_forward(const void* x, const void* w, void* out, long long
     if (!x || !w || !out) return fail("null pointer");
     if (B < 1 || N < 1) return fail("invalid shape B=%lld N=%lld", B, N);
     g_err[0] = 0;
-    const long long total = B * N;
-    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    sml::wirtinger_mul_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float2*)x, (const float2*)w, (float2*)out, B, N);
+    const long long nb = ((N + 1) / 2 + 255) / 256;
+    // enough batch slices to fill the machine (148 SMs x 8 CTAs) when N alone does not
+    long long by = (148 * 8 + nb - 1) / nb;
+    if (by > B) by = B;
+    if (by > 65535) by = 65535;
+    sml::wirtinger_mul_fwd_kernel<<<dim3((unsigned)nb, (unsigned)by), 256, 0, (cudaStream_t)stream>>>((const float2*)x, (const float2*)w, (float2*)out, B, N);
     count_launch();
     SML_CUDA(cudaGetLastError());
     return 0;
@@ -942,9 +947,11 @@ int sml_wirtinger_filter_forward(const void* x_freq, const float* w_re, const fl
     if (B < 1 || T < 1 || D < 1 || F < 1) return fail("invalid shape B=%d T=%d D=%d F=%d", B, T, D, F);
     g_err[0] = 0;
     const int k = F < T / 2 ? F : T / 2;
-    const long long total = (long long)B * T * D;
-    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    sml::wirtinger_filter_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float2*)x_freq, w_re, w_im, (float2*)out, B, T, D, F, k);
+    dim3 blk(32, 8), grid((D + 31) / 32, (T + 7) / 8, 1);
+    long long bz = (148ll * 8 + (long long)grid.x * grid.y - 1) / ((long long)grid.x * grid.y);
+    grid.z = (unsigned)(bz > B ? B : (bz > 65535 ? 65535 : bz));
+    if ((T + 7) / 8 > 65535) return fail("T too large for this entry point");
+    sml::wirtinger_filter_fwd_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>((const float2*)x_freq, w_re, w_im, (float2*)out, B, T, D, F, k);
     count_launch();
     SML_CUDA(cudaGetLastError());
     return 0;
@@ -957,9 +964,9 @@ int sml_wirtinger_filter_backward(const void* g, const void* x_freq, const float
     g_err[0] = 0;
     const int k = F < T / 2 ? F : T / 2;
     cudaStream_t s = (cudaStream_t)stream;
-    SML_CUDA(cudaMemsetAsync(gw_re, 0, sizeof(float) * (size_t)D * F, s));
-    SML_CUDA(cudaMemsetAsync(gw_im, 0, sizeof(float) * (size_t)D * F, s));
-    dim3 blk(32, 8), grid((D + 31) / 32, (T + 7) / 8);
+    const int rows = T > F ? T : F;      // rows f < T carry gx, rows f < F carry the gradient columns (zero beyond k)
+    dim3 blk(32, 8), grid((D + 31) / 32, (rows + 7) / 8);
+    if ((rows + 7) / 8 > 65535) return fail("T / F too large for this entry point");
     sml::wirtinger_filter_bwd_kernel<<<grid, blk, 0, s>>>((const float2*)g, (const float2*)x_freq, w_re, w_im, (float2*)gx, gw_re, gw_im, B, T, D, F, k);
     count_launch();
     SML_CUDA(cudaGetLastError());

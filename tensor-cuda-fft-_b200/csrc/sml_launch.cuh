@@ -87,6 +87,8 @@ int launch_fast_ext(const Plan& p, const CUtensorMap& map_in, const CUtensorMap&
     if (p.NR == NR_ && p.KJ == KJ_ && p.P == P_ && p.ctas_per_sm == MINB_) return launch_fast_inst<NR_, KJ_, P_, MINB_, IO, BWD, true>(map_in, map_out, map_res, prm, grid, stream, p.xb);
     SML_CASE(32, 8, 4, 2)
     SML_CASE(32, 12, 4, 2)
+    SML_CASE(32, 8, 4, 3)
+    SML_CASE(32, 12, 4, 3)
     SML_CASE(32, 16, 4, 2)
     SML_CASE(32, 24, 4, 2)
     SML_CASE(32, 32, 4, 2)
