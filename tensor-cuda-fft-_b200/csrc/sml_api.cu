@@ -45,6 +45,7 @@ const Knobs& knobs() {
         if (const char* e = getenv("SML_TC")) v.tc = atoi(e) != 0 ? 1 : 0;
         if (const char* e = getenv("SML_PDL")) v.pdl = atoi(e) != 0 ? 1 : 0;
         if (const char* e = getenv("SML_EXT_CTAS")) v.ext_ctas = atoi(e);
+        if (const char* e = getenv("SML_SPLIT")) v.split = atoi(e);
         return v;
     }();
     return k;
@@ -74,6 +75,7 @@ using sml_host::get_encode_fn;
 using sml_host::knobs;
 using sml_host::launch_fast;
 using sml_host::launch_fast_ext;
+using sml_host::launch_fast_split;
 using sml_host::Plan;
 
 #define SML_CUDA(expr)                                                                         \
@@ -86,10 +88,15 @@ using sml_host::Plan;
 // ------------------------------------------------------------------------------------------------
 // per-device state
 // ------------------------------------------------------------------------------------------------
+struct SplitScratch {   // pass splitting: partial bands + arrival counters, one per (device, stream)
+    char* buf = nullptr;
+    size_t cap = 0;
+};
 struct DeviceState {
     int sm_count = 0;
     int cc_major = 0;
     std::map<int, sml::cf*> twiddles;   // T -> W_T^n table
+    std::map<cudaStream_t, SplitScratch> split;
 };
 std::mutex g_mu;
 std::map<int, DeviceState> g_dev;
@@ -147,6 +154,57 @@ int twiddle_table(DeviceState* st, int T, cudaStream_t stream, const sml::cf** o
         it = st->twiddles.emplace(T, tab).first;
     }
     *out = it->second;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass splitting (sml_fast.cuh): when a launch has fewer work items than half the resident CTA slots -- long sequences
+// with a small batch per rank: T = 128K holds 128 items per batch element for 296 CTA slots -- `split` CTAs share one item,
+// each streaming R / split consecutive passes; the partial bands are exchanged through an L2-resident scratch block.
+// ------------------------------------------------------------------------------------------------
+int choose_split(int ntiles, int slots, int R) {
+    if (knobs().split > 0) {
+        int s = knobs().split;
+        while (s > 1 && (R % s != 0)) s >>= 1;
+        return s < 1 ? 1 : s;
+    }
+    int s = 1;
+    // Measured on B200 (D = 1024: 128 items per batch element on 296 CTA slots; profiles/r02_pass_splitting.md): splitting pays only
+    // while the units still fit into ONE round of resident CTAs -- B = 1, T = 128K: 0.967 ms unsplit, 0.614 (S = 2), 0.627 (4), 0.701
+    // (8), 0.879 (16); with 256 or more items S = 1 wins (every member re-reads all S partial bands and repeats the mid phase).
+    // So: the largest power of two that divides R, leaves at least 4 passes per CTA and keeps items * S within the resident slots.
+    while ((long long)ntiles * (2 * s) <= (long long)slots && R % (2 * s) == 0 && R / (2 * s) >= 4 && s < 8) s *= 2;
+    return s;
+}
+// scratch of a split launch: [units][2 KJ][threads] complex partial bands, then one arrival counter per work item (cleared here).
+// Cached per (device, stream); grown on demand (like the twiddle tables: not while the stream is being captured).
+int setup_split(DeviceState* st, const Plan& p, sml::FastParams* prm, int slots, cudaStream_t stream, bool ext = false) {
+    prm->split = (p.NR == 32 && !ext) ? choose_split(prm->ntiles, slots, p.R) : 1;   // instantiated for the largest sub-transform only
+    prm->xch = nullptr;
+    prm->xflag = nullptr;
+    if (prm->split <= 1) { prm->split = 1; return 0; }
+    const size_t band = sizeof(sml::cf) * (size_t)prm->ntiles * prm->split * (2 * p.KJ) * (size_t)(p.NR * p.P);
+    const size_t flags = sizeof(unsigned int) * (size_t)prm->ntiles;
+    const size_t need = ((band + 255) & ~(size_t)255) + flags;
+    char* buf = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        SplitScratch& sc = st->split[stream];
+        if (sc.cap < need) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+                prm->split = 1;   // no allocation inside a capture: this launch (and the graph) runs unsplit -- same results
+                return 0;
+            }
+            if (sc.buf) { SML_CUDA(cudaStreamSynchronize(stream)); cudaFree(sc.buf); sc.buf = nullptr; sc.cap = 0; }
+            SML_CUDA(cudaMalloc(&sc.buf, need));
+            sc.cap = need;
+        }
+        buf = sc.buf;
+    }
+    prm->xch = reinterpret_cast<sml::cf*>(buf);
+    prm->xflag = reinterpret_cast<unsigned int*>(buf + ((band + 255) & ~(size_t)255));
+    SML_CUDA(cudaMemsetAsync(prm->xflag, 0, flags, stream));
     return 0;
 }
 
@@ -262,7 +320,10 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
         prm.invT = invT;
         prm.dbg = debug_record();
         const int slots = st->sm_count * p.ctas_per_sm;
-        const int grid = prm.ntiles < slots ? prm.ntiles : slots;
+        if (setup_split(st, p, &prm, slots, stream)) return 1;
+        const int units = prm.ntiles * prm.split;
+        const int grid = units < slots ? units : slots;
+        if (prm.split > 1) return launch_fast_split<IO, false>(p, map, map_out, prm, grid, stream);
         return launch_fast<IO, false>(p, map, map_out, prm, grid, stream);
     }
     // generic path
@@ -354,8 +415,10 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         prm.invT = invT;
         prm.dbg = debug_record();
         const int slots = st->sm_count * p.ctas_per_sm;
-        const int grid = prm.ntiles < slots ? prm.ntiles : slots;
-        if (launch_fast<IO, true>(p, map, map_out, prm, grid, stream)) return 1;
+        if (setup_split(st, p, &prm, slots, stream)) return 1;
+        const int units = prm.ntiles * prm.split;
+        const int grid = units < slots ? units : slots;
+        if (prm.split > 1 ? launch_fast_split<IO, true>(p, map, map_out, prm, grid, stream) : launch_fast<IO, true>(p, map, map_out, prm, grid, stream)) return 1;
         if (want_grads && launch_filtergrad_reduce(prm.gpart, prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k, flat_mc, flat_next, stream)) return 1;
         return 0;
     }
@@ -478,7 +541,9 @@ int ext_impl(const void* in, const float* w_re, const float* w_im, const float* 
     if (row0_out != 0) return fail("the backward of a problem with in_row0 != 0 is not supported (its output rows would start at a shifted row)");
     prm.in_q = row0_in / p.R; prm.in_r = row0_in % p.R;
     const int slots = st->sm_count * p.ctas_per_sm;
-    const int grid = prm.ntiles < slots ? prm.ntiles : slots;
+    if (setup_split(st, p, &prm, slots, stream, true)) return 1;
+    const int units = prm.ntiles * prm.split;
+    const int grid = units < slots ? units : slots;
     if (launch_fast_ext<IO, BWD>(p, map_in, map_out, map_res, prm, grid, stream)) return 1;
     if (want_grads && launch_filtergrad_reduce(prm.gpart, prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k, nullptr, nullptr, stream)) return 1;
     return 0;
@@ -909,6 +974,8 @@ int sml_release(void) {
         for (auto& dv : g_dev) {
             for (auto& kv : dv.second.twiddles) cudaFree(kv.second);
             dv.second.twiddles.clear();
+            for (auto& kv : dv.second.split) cudaFree(kv.second.buf);
+            dv.second.split.clear();
         }
     }
     return sml_host::tc_release_tables();

@@ -52,6 +52,11 @@ struct FastParams {
     int ntiles;            // B * ntd
     float invT;
     unsigned int* dbg;     // host-mapped debug record (null unless SML_DEBUG is set): filled by a timed-out mbarrier wait
+    // ---- pass splitting: `split` CTAs share one work item, each streams R / split consecutive passes; the partial bands meet in
+    //      `xch` (one [2 KJ][threads] complex block per unit, L2-resident) and are summed by every CTA of the group in a fixed order
+    int split;             // 1 = off
+    cf* xch;               // (ntiles * split) partial bands
+    unsigned int* xflag;   // (ntiles) arrival counters, zero before the launch
     // ---- extended kernels (template flag EXT) only: the hosting block's prologue / epilogue fused around the transform ----
     const float2* stats;   // (B, T) {mean, rstd} per TRANSFORM row ({0,0} on zero-padding rows): LayerNorm on load, or null
     const float* scale;    // (B, D) per (batch element, channel) factor on the filtered spectrum (context gate), or null
@@ -249,12 +254,14 @@ __device__ __forceinline__ void prefetch_xlow_l2(const FastParams& prm, int b, i
 // filter gradient terms G conj(X) (reference wirtinger_ops.py:77-80), one per batch element (summed by
 // filtergrad_reduce_kernel).
 // ------------------------------------------------------------------------------------------------
+// side = false (pass splitting: every CTA of a group runs the mid phase on the same summed band): skip the global side outputs
+// (X_low, gradient terms, the bin T/2), which the first CTA of the group writes.
 template <int NR, int KJ, bool BWD, bool EXT = false>
-__device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const FastParams& prm, int b, int d0, int ff1, int lane) {
+__device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const FastParams& prm, int b, int d0, int ff1, int lane, bool side = true) {
     constexpr int NJ = 2 * KJ;
     const int D = prm.D;
     const bool pvalid = d0 < D;
-    const bool grads = BWD && prm.gw_re != nullptr;
+    const bool grads = BWD && prm.gw_re != nullptr && side;
     // EXT: per-(batch element, channel) factor on the filtered spectrum, and the raw analysis value of the bin -T/2
     float sc0 = 1.f, sc1 = 1.f;
     cf znyq = cf{0.f, 0.f};
@@ -321,7 +328,7 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
             }
             cf a0, a1;
             if constexpr (!BWD) {
-                if (live && prm.xlow != nullptr) {
+                if (live && prm.xlow != nullptr && side) {
                     reinterpret_cast<float2*>(prm.xlow)[xrow0 + af] = make_float2(s0.re, s0.im);
                     reinterpret_cast<float2*>(prm.xlow)[xrow1 + af] = make_float2(s1.re, s1.im);
                 }
@@ -381,13 +388,13 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
                 const float wn0 = __ldg(prm.wnyq + d0), wn1 = __ldg(prm.wnyq + d0 + 1);
                 const size_t o = (size_t)b * D + d0;
                 if constexpr (!BWD) {
-                    if (prm.xnyq != nullptr) { prm.xnyq[o] = znyq.re; prm.xnyq[o + 1] = znyq.im; }
+                    if (prm.xnyq != nullptr && side) { prm.xnyq[o] = znyq.re; prm.xnyq[o + 1] = znyq.im; }
                     float b0 = 0.f, b1 = 0.f;
                     if (prm.sb_nyq != nullptr) { b0 = __ldg(prm.sb_nyq + d0); b1 = __ldg(prm.sb_nyq + d0 + 1); }
                     c = cf{(znyq.re * wn0 + b0) * sc0 * prm.invT, (znyq.im * wn1 + b1) * sc1 * prm.invT};
                 } else {
                     const float g0 = znyq.re * sc0, g1 = znyq.im * sc1;
-                    if (prm.gnyqpart != nullptr && prm.xnyq != nullptr) {
+                    if (prm.gnyqpart != nullptr && prm.xnyq != nullptr && side) {
                         prm.gnyqpart[o] = g0 * prm.xnyq[o] * prm.invT;
                         prm.gnyqpart[o + 1] = g1 * prm.xnyq[o + 1] * prm.invT;
                     }
@@ -435,7 +442,9 @@ __host__ __device__ constexpr bool band_first(int j) {
 //     full half-spectrum multiplier) -- the causal FFT-convolution core of fft_lm's FixedSpectralBlock.
 // With a residual the load stream of a work item is R analysis loads followed by R residual loads, all through the same XB
 // landing tiles and mbarriers (load n -> tile n % XB).
-template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, int XB, bool EXT = false>
+// SPLIT = true: pass splitting (FastParams::split CTAs share one work item); compiled only for the largest sub-transform, where
+// long sequences leave the grid under-filled -- as a run-time option it cost the default forward kernel 2.7 % (10 more registers).
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, int XB, bool EXT = false, bool SPLIT = false>
 __global__ void __launch_bounds__(NR* P, MINB)
     sml_fast_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                     const __grid_constant__ CUtensorMap tmap_res, const FastParams prm) {
@@ -470,9 +479,12 @@ __global__ void __launch_bounds__(NR* P, MINB)
     const int R = prm.R, T = prm.T, D = prm.D;
     const float2* const gtab = reinterpret_cast<const float2*>(prm.gtab);
 
-    const int my_ntiles = (prm.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // work units: (work item, group member j); member j streams the passes [j Rs, (j + 1) Rs) of the item (split = 1: Rs = R)
+    const int S = SPLIT ? prm.split : 1, Rs = SPLIT ? R / S : R;
+    const int nunits = prm.ntiles * S;
+    const int my_ntiles = (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // units of this CTA
     const bool res = EXT && prm.res != 0;        // residual rows ride through the landing tiles during synthesis
-    const int lpi = res ? 2 * R : R;             // loads per work item
+    const int lpi = res ? 2 * Rs : Rs;           // loads per unit
     const int total_loads = my_ntiles * lpi;
 
     // rows of pass r in a tensor whose row i is transform row row0 + i (row0 = R*q0 + r0): t - row0 = R*(m - q0 - borrow) + rs
@@ -485,9 +497,11 @@ __global__ void __launch_bounds__(NR* P, MINB)
         if (L >= total_loads) return;
         const int it = L / lpi;
         int r = L - it * lpi;
-        const bool resload = r >= R;
-        if (resload) r -= R;
-        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const bool resload = r >= Rs;
+        if (resload) r -= Rs;
+        const int unit = (int)blockIdx.x + it * (int)gridDim.x;
+        const int tile = unit / S;
+        r += (unit - tile * S) * Rs;
         const int b = tile / prm.ntd, dt = tile - b * prm.ntd;
         int rs = r, mshift = 0;
         if constexpr (EXT) { if (!resload) shifted(r, prm.in_q, prm.in_r, rs, mshift); }   // residual rows: output geometry, no shift
@@ -538,22 +552,25 @@ __global__ void __launch_bounds__(NR* P, MINB)
     int slot = 0;   // cj slot of the current pass
 
     for (int it = 0; it < my_ntiles; ++it) {
-        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int unit = (int)blockIdx.x + it * (int)gridDim.x;
+        const int tile = unit / S;
+        const int member = unit - tile * S;
+        const int r_begin = member * Rs, r_end = r_begin + Rs;
         const int b = tile / prm.ntd, dt = tile - b * prm.ntd;
 
         cf acc[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[j] = cf{0.f, 0.f};
-        if constexpr (BWD) prefetch_xlow_l2<NR, KJ>(prm, b, dt * 2 * P + 2 * fp2, ff1);
+        if constexpr (BWD) { if (member == 0) prefetch_xlow_l2<NR, KJ>(prm, b, dt * 2 * P + 2 * fp2, ff1); }
 
         // ===================== analysis: R streamed passes, band accumulated in registers =====================
-        for (int r = 0; r < R; ++r) {
+        for (int r = r_begin; r < r_end; ++r) {
             // twiddle seeds for this pass (consumed after the first DFT / after barrier (A))
             const float2 wb = __ldg(gtab + (R * tm2 + r));   // W_T^{R m2 + r}
             float2 cjv = make_float2(1.f, 0.f), cjn = make_float2(1.f, 0.f);
             if (tid < NJ) {
                 cjv = cj_load(r);
-                if (r + 1 == R) cjn = cj_load(0);   // first synthesis pass
+                if (r + 1 == r_end) cjn = cj_load(r_begin);   // first synthesis pass
             }
             cf v[NR];
             bool ln_done = false;
@@ -585,7 +602,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
             // the last warp to drain the tile re-arms it right away with the next load that lands there (XB ahead).  The tile
             // of a work item's last pass becomes the store staging buffer instead and is re-armed after the last store
             // (with a residual and two tiles it takes a residual load right away: staging alternates between the tiles).
-            if (r + 1 < R || (res && XB == 2)) {
+            if (r + 1 < r_end || (res && XB == 2)) {
                 __syncwarp();
                 if ((tid & 31) == 0) {
                     __threadfence_block();
@@ -602,7 +619,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
             }
             if (tid < NJ) {
                 cj[slot * CJN + tid] = cf{cjv.x, cjv.y};
-                if (r + 1 == R) cj[(slot ^ 1) * CJN + tid] = cf{cjn.x, cjn.y};
+                if (r + 1 == r_end) cj[(slot ^ 1) * CJN + tid] = cf{cjn.x, cjn.y};
             }
             __syncthreads();   // (B)
             {
@@ -621,18 +638,55 @@ __global__ void __launch_bounds__(NR* P, MINB)
         }
 
         // ===================== mid phase: un-mix the channel pair, filter, re-pack =====================
-        spectral_mid_phase<NR, KJ, BWD, EXT>(acc, prm, b, dt * 2 * P + 2 * fp2, ff1, tid & 31);
+        if (SPLIT && S > 1) {
+            // pass splitting: publish this unit's partial band, wait for the group, sum the S partials in member order (every
+            // CTA of the group gets the same bits); all CTAs of the grid are co-resident (grid <= resident slots), so the wait
+            // cannot starve.  Bounded like the mbarrier waits: a lost arrival traps instead of hanging the GPU.
+            cf* const mine = prm.xch + (size_t)unit * NJ * NT;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) __stcg(reinterpret_cast<float2*>(mine + (size_t)j * NT + tid), make_float2(acc[j].re, acc[j].im));
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                atomicAdd(prm.xflag + tile, 1u);
+                uint64_t t0 = 0;
+                for (uint32_t spins = 1;; ++spins) {
+                    unsigned int seen;
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(prm.xflag + tile) : "memory");
+                    if (seen >= (unsigned int)S) break;
+                    __nanosleep(64);
+                    if ((spins & 0x3FFFu) == 0u) {
+                        uint64_t now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > 10000000000ull) mbar_timeout(prm.dbg, 3u, seen, (uint32_t)tile);
+                    }
+                }
+            }
+            __syncthreads();
+            const cf* const grp = prm.xch + (size_t)tile * S * NJ * NT;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[j] = cf{0.f, 0.f};
+            for (int m = 0; m < S; ++m) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const float2 v2 = __ldcg(reinterpret_cast<const float2*>(grp + ((size_t)m * NJ + j) * NT + tid));
+                    acc[j] = cf{acc[j].re + v2.x, acc[j].im + v2.y};
+                }
+            }
+        }
+        spectral_mid_phase<NR, KJ, BWD, EXT>(acc, prm, b, dt * 2 * P + 2 * fp2, ff1, tid & 31, member == 0);
 
         // ===================== synthesis: transpose of analysis; rows leave through a TMA store from X =====================
         // staging tile: the tile of this work item's last load, drained by every warp (barrier (A')); with a residual the
         // tile that received (or is about to receive) the residual rows of the pass: load L
-        for (int r = 0; r < R; ++r) {
+        for (int r = r_begin; r < r_end; ++r) {
             unsigned char* const stage = res ? xbuf(L) : xbuf(L - 1);
             // twiddle seeds: v[m2] *= conj(W_T^{r f1} * (W_T^{R f1})^{m2})
             const float2 sr = __ldg(gtab + r * ff1);
             const float2 beta = __ldg(gtab + R * ff1);
             float2 cjn = make_float2(1.f, 0.f);
-            if (tid < NJ && r + 1 < R) cjn = cj_load(r + 1);
+            if (tid < NJ && r + 1 < r_end) cjn = cj_load(r + 1);
             cf v[NR];
             {
                 const cf* cjs = cj + slot * CJN;
@@ -654,14 +708,14 @@ __global__ void __launch_bounds__(NR* P, MINB)
 #pragma unroll
                 for (int m2 = 0; m2 < NR; ++m2) xb[m2 * P * XS] = v[m2];
             }
-            if (tid < NJ && r + 1 < R) cj[(slot ^ 1) * CJN + tid] = cf{cjn.x, cjn.y};
+            if (tid < NJ && r + 1 < r_end) cj[(slot ^ 1) * CJN + tid] = cf{cjn.x, cjn.y};
             if (tid == 0) {
-                if (r > 0) tma_store_wait_read();   // X may be overwritten after (B')
+                if (r > r_begin) tma_store_wait_read();   // X may be overwritten after (B')
                 if (res) {
                     // one tile: fetch this pass's residual rows now (the tile is free: drained / its last store has been read);
                     // two tiles: the tile of pass r - 1 is free, it takes the residual rows of pass r + 1
                     if (XB == 1) issue_load(L);
-                    else if (r > 0) issue_load(L + 1);
+                    else if (r > r_begin) issue_load(L + 1);
                 }
             }
             __syncthreads();   // (B')

@@ -24,6 +24,7 @@ struct Knobs {
     int fast_ctas = 0;   // 2 or 3: CTAs per SM of the NR = 32, KJ = 12 kernel (0 = default)
     int fast_xb = 0;     // 1 or 2: TMA landing tiles (0 = default)
     int tc = -1;         // 0 / 1: tensor-core kernel for eligible bf16 problems (-1 = default)
+    int split = 0;       // SML_SPLIT: CTAs per work item of the pass-splitting schedule (0 = choose by the fill of the grid, 1 = off)
     int ext_ctas = 0;    // 2 or 3: CTAs per SM of the extended NR = 32, KJ <= 12 kernels (0 = default)
     int pdl = 0;         // SML_PDL=1: launch with programmatic dependent launch (measured slower inside the fwd/bwd/reduce chain: off by default)
 };
@@ -78,6 +79,10 @@ void count_launch(int n = 1);
 template <typename IO, bool BWD>
 int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
                 cudaStream_t stream);
+// the pass-splitting kernels, instantiated in sml_inst_split_*.cu
+template <typename IO, bool BWD>
+int launch_fast_split(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
+                      cudaStream_t stream);
 // the extended kernels (block prologue / epilogue fused in), instantiated in sml_inst_ext_*.cu
 template <typename IO, bool BWD>
 int launch_fast_ext(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const CUtensorMap& map_res,

@@ -1,0 +1,6 @@
+// explicit instantiation of the pass-splitting fused kernels for IO = float, BWD = false (see sml_launch.cuh)
+#include "sml_launch.cuh"
+
+namespace sml_host {
+template int launch_fast_split<float, false>(const Plan&, const CUtensorMap&, const CUtensorMap&, const sml::FastParams&, int, cudaStream_t);
+}

@@ -32,11 +32,11 @@ int ensure_smem_attr(Kern kern, size_t smem_bytes, std::atomic<unsigned long lon
 template <int NR, int P, int MINB, typename IO>
 constexpr bool xb2_fits() { return (sml::FastCfg<NR, P, IO, 2>::SMEM_BYTES + 1024) * MINB <= 227u * 1024u; }
 
-template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, int XB, bool EXT>
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, int XB, bool EXT, bool SPLIT = false>
 int launch_fast_xb(const CUtensorMap& map_in, const CUtensorMap& map_out, const CUtensorMap& map_res, const sml::FastParams& prm,
                    int grid, cudaStream_t stream) {
     using C = sml::FastCfg<NR, P, IO, XB>;
-    auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD, XB, EXT>;
+    auto kern = sml::sml_fast_kernel<NR, KJ, P, MINB, IO, BWD, XB, EXT, SPLIT>;
     static std::atomic<unsigned long long> attr_done{0};   // per kernel instantiation (this function template)
     if (int rc = ensure_smem_attr(kern, C::SMEM_BYTES, attr_done)) return rc;
     SML_CUDA(launch_pdl(kern, dim3(grid), dim3(C::NT), C::SMEM_BYTES, stream, map_in, map_out, map_res, prm));
@@ -44,13 +44,13 @@ int launch_fast_xb(const CUtensorMap& map_in, const CUtensorMap& map_out, const 
     return 0;
 }
 
-template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, bool EXT>
+template <int NR, int KJ, int P, int MINB, typename IO, bool BWD, bool EXT, bool SPLIT = false>
 int launch_fast_inst(const CUtensorMap& map_in, const CUtensorMap& map_out, const CUtensorMap& map_res, const sml::FastParams& prm,
                      int grid, cudaStream_t stream, int xb) {
     if constexpr (xb2_fits<NR, P, MINB, IO>()) {
-        if (xb == 2) return launch_fast_xb<NR, KJ, P, MINB, IO, BWD, 2, EXT>(map_in, map_out, map_res, prm, grid, stream);
+        if (xb == 2) return launch_fast_xb<NR, KJ, P, MINB, IO, BWD, 2, EXT, SPLIT>(map_in, map_out, map_res, prm, grid, stream);
     }
-    return launch_fast_xb<NR, KJ, P, MINB, IO, BWD, 1, EXT>(map_in, map_out, map_res, prm, grid, stream);
+    return launch_fast_xb<NR, KJ, P, MINB, IO, BWD, 1, EXT, SPLIT>(map_in, map_out, map_res, prm, grid, stream);
 }
 
 template <typename IO, bool BWD>
@@ -75,6 +75,22 @@ int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map
     SML_CASE(8, 16, 32, 2)
 #undef SML_CASE
     return fail("internal: no fast kernel for NR=%d KJ=%d P=%d", p.NR, p.KJ, p.P);
+}
+
+// pass-splitting kernels (SPLIT = true, sml_fast.cuh): the largest sub-transform only (T = R * 1024: the long sequences)
+template <typename IO, bool BWD>
+int launch_fast_split(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map_out, const sml::FastParams& prm, int grid,
+                      cudaStream_t stream) {
+#define SML_CASE(NR_, KJ_, P_, MINB_) \
+    if (p.NR == NR_ && p.KJ == KJ_ && p.P == P_ && p.ctas_per_sm == MINB_) return launch_fast_inst<NR_, KJ_, P_, MINB_, IO, BWD, false, true>(map_in, map_out, map_in, prm, grid, stream, p.xb);
+    SML_CASE(32, 8, 4, 3)
+    SML_CASE(32, 12, 4, 3)
+    SML_CASE(32, 16, 4, 2)
+    SML_CASE(32, 24, 4, 2)
+    SML_CASE(32, 32, 4, 2)
+    SML_CASE(32, 12, 4, 2)
+#undef SML_CASE
+    return fail("internal: no pass-splitting kernel for NR=%d KJ=%d P=%d", p.NR, p.KJ, p.P);
 }
 
 // extended kernels (EXT = true: LayerNorm on load, residual on store, row windows, channel scale, bin T/2; sml_fast.cuh).  The
