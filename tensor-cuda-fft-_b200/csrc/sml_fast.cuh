@@ -507,14 +507,22 @@ __global__ void __launch_bounds__(NR* P, MINB)
         if constexpr (EXT) { if (!resload) shifted(r, prm.in_q, prm.in_r, rs, mshift); }   // residual rows: output geometry, no shift
         const CUtensorMap* const tm = (EXT && resload) ? &tmap_res : &tmap_in;
         fence_proxy_async();
+#ifdef SML_DIAG_NO_LOAD   // diagnostic build (tools/diag_no_io.sh): the SM side alone, tiles "land" at once with whatever is in shared memory
+        (void)tm; (void)rs; (void)mshift; (void)b; (void)dt;
+        mbar_arrive(mbar + xslot(L));
+#else
         mbar_expect_tx(mbar + xslot(L), C::LOAD_BYTES);
 #pragma unroll
         for (int bx = 0; bx < C::NBOX; ++bx)
             tma_load_4d(xbuf(L) + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), tm, mbar + xslot(L), dt * 2 * P, rs, bx * C::BOXROWS - mshift, b);
+#endif
     };
     // (stores are never shifted: TMA tensor stores fault on negative coordinates -- measured -- so an output window that
     //  does not start at transform row 0 is expressed as a phase ramp on the filter by the host instead)
     auto issue_store = [&](const unsigned char* stage, int b, int dt, int r) {   // thread 0 only: staging tile -> rows r + R*m
+#ifdef SML_DIAG_NO_STORE
+        if (r >= 0) return;
+#endif
 #pragma unroll
         for (int bx = 0; bx < C::NBOX; ++bx)
             tma_store_4d(&tmap_out, stage + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), dt * 2 * P, r, bx * C::BOXROWS, b);
