@@ -128,9 +128,11 @@ class _CausalSpectralConvFn(torch.autograd.Function):
         d_beta = dpooled.sum(0)
         dmhat = dpooled * gamma.float()                       # d/d(mean_t x^): spreads over the T rows as dmhat / T
         # beta path: y_beta[b,t,c] = s[b,c] * beta_gain[c] * u[t]
-        gs = torch.einsum("btc,bc->tc", gf, s)                # sum_b g * s
-        d_beta_gain = (gs * u.float()[:, None]).sum(0)
-        d_u = gs @ beta_gain.float()
+        # two batched matrix-vector products over g (one read each) instead of a (T, C) intermediate:
+        #   d_beta_gain[c] = sum_b s[b,c] * (u^T g[b])[c] ;  d_u[t] = sum_b (g[b] (s[b] * beta_gain))[t]
+        ug = torch.matmul(u.to(gc.dtype), gc).float()                                   # (B, C)
+        d_beta_gain = (ug * s).sum(0)
+        d_u = torch.bmm(gc, (s * beta_gain.float()).to(gc.dtype).unsqueeze(2)).squeeze(2).float().sum(0)
         # LayerNorm backward (+ the skip connection's gradient, + the pooled-mean term) in one pass
         # (the pooled-mean term enters dL/dx^ as the per-(b, c) constant dmhat / T: chan_add of the same kernel)
         chan_add = (dmhat / T).contiguous()
@@ -175,8 +177,7 @@ def _kernel_filter(H: torch.Tensor, chan: torch.Tensor):
     """(w_re, w_im, w_nyq) of the fused kernel for the irfft multiplier chan[c] * H[f]: the kernel takes Re(ifft(.)) of a
     one-sided spectrum (bins >= 1 at half weight, spectral_layers.py:112), so bins 1..n/2-1 enter doubled."""
     Fn = H.shape[0] - 1
-    two = torch.full((Fn,), 2.0, device=H.device)
-    two[0] = 1.0
+    two = torch.cat([torch.ones(1, device=H.device), torch.full((Fn - 1,), 2.0, device=H.device)])   # (no indexed scalar stores: graph-capturable)
     Hs = H[:Fn] * two
     w_re = chan[:, None] * Hs.real[None, :]
     w_im = chan[:, None] * Hs.imag[None, :]
@@ -233,8 +234,7 @@ class FixedSpectralBlock(nn.Module):
         gain = self.gain.float()
         w_re, w_im, w_nyq = _kernel_filter(H, gamma * gain)
         # beta path: a LayerNorm bias on the T real rows of a zero-padded window is beta * rect_T
-        rect = torch.zeros(n, device=x.device)
-        rect[:T] = 1.0
+        rect = torch.cat([torch.ones(T, device=x.device), torch.zeros(n - T, device=x.device)])
         Q = torch.fft.rfft(rect) * H
         u = torch.fft.irfft(Q, n=n)[:T]
         q_re, q_im, q_nyq = _kernel_filter(Q.detach(), torch.ones(1, device=x.device))
@@ -249,6 +249,39 @@ class FixedSpectralBlock(nn.Module):
         x = self.spectral_half(x, cutoff)
         ff_in = self.ffn_ln(x)
         return x + self.drop(self.ffn(ff_in))
+
+    def graphed(self, sample: torch.Tensor, cutoff: Optional[int] = None, half_only: bool = False, num_warmup_iters: int = 3):
+        """A CUDA-graph-captured callable of this block (or of its spectral half) for inputs of ``sample``'s shape: forward and
+        backward replay as graphs.  The block's spectral half is two fused kernels surrounded by a few dozen small parameter-side
+        ops (effective filter, gates, reductions): at the reference's sizes their launch cost is most of the step, a graph
+        removes it.  Usual CUDA-graph rules: fixed shape and cutoff, dropout inactive."""
+        if not sample.is_cuda:
+            raise RuntimeError("FixedSpectralBlock (B200 build) needs a CUDA tensor; there is no CPU path")
+        if self.training and self.drop.p > 0.0:
+            raise RuntimeError("graphed(): dropout draws new random numbers per call; use eval() or dropout=0")
+        outer = self
+
+        class _Half(nn.Module):      # only the parameters the spectral half uses (make_graphed_callables wants every one used)
+            def __init__(self):
+                super().__init__()
+                self.ln, self.drop, self.gate_ctx = outer.ln, outer.drop, outer.gate_ctx
+                self.kernel, self.gain, self.gate_freq_logits = outer.kernel, outer.gain, outer.gate_freq_logits
+                self.kernel_len, self.transition_bins = outer.kernel_len, outer.transition_bins
+                self.train(outer.training)
+
+            def forward(self, x):
+                return FixedSpectralBlock.spectral_half(self, x, cutoff)
+
+        class _Whole(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.blk = outer
+
+            def forward(self, x):
+                return self.blk(x, cutoff)
+
+        mod = _Half() if half_only else _Whole()
+        return torch.cuda.make_graphed_callables(mod, (sample.detach().clone().requires_grad_(True),), num_warmup_iters=num_warmup_iters)
 
 
 @torch.no_grad()

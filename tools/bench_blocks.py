@@ -107,9 +107,22 @@ def main():
         fo = time_ms(lambda: blk.spectral_half(x2), args.steps, args.warmup)
     mo = time_ms(ours, args.steps, args.warmup)
     mr = time_ms(ref_composition, max(args.steps // 5, 3), 2)
+    try:
+        gh = blk.graphed(x2, half_only=True)
+
+        def ours_graphed():
+            for p in blk.parameters():
+                p.grad = None
+            xr = x2.detach().requires_grad_(True)
+            gh(xr).backward(g2)
+
+        mg = time_ms(ours_graphed, args.steps, args.warmup)
+    except Exception as e:
+        print("graphed f-2 unavailable:", str(e).splitlines()[0][:200], file=sys.stderr)
+        mg = None
     act2 = B * T * C * esz
     print(json.dumps({"row": "f-2 FixedSpectralBlock spectral half", "shape": [B, T, C], "kernel_len": K, "n_fft": sc.conv_fft_len(T, K),
-                      "dtype": args.dtype, "fwd_ms": round(fo, 4), "fwd_bwd_ms": round(mo, 4),
+                      "dtype": args.dtype, "fwd_ms": round(fo, 4), "fwd_bwd_ms": round(mo, 4), "fwd_bwd_graphed_ms": None if mg is None else round(mg, 4),
                       "reference_composition_on_gpu_fwd_bwd_ms": round(mr, 4), "tokens_per_s": B * T / (mo * 1e-3),
                       "floor_passes": 5, "frac_of_hbm_roofline": 5 * act2 / (mo * 1e-3) / 1e9 / args.peak}))
 
