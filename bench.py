@@ -629,6 +629,19 @@ def run_blocks(prob, B, T, D, roof, barrier):
     ms = time_steps(conv_step, 30, 5, barrier)
     out["fixed_block_half"] = {"shape": [Bc, Tc, C], "kernel_len": K, "n_fft": sc.conv_fft_len(Tc, K), "ms_per_step": ms,
                                "value": Bc * Tc / (ms * 1e-3), "unit": UNIT, "roofline_5pass": roof(5 * Bc * Tc * C * 4, ms)}
+    try:      # the same step replayed from CUDA graphs: the half is two fused kernels plus a few dozen small parameter-side ops
+        gh = blk.graphed(x2, half_only=True)
+
+        def conv_step_graphed():
+            for p in blk.parameters():
+                p.grad = None
+            xr = x2.detach().requires_grad_(True)
+            gh(xr).backward(g2)
+
+        ms_g = time_steps(conv_step_graphed, 30, 5, barrier)
+        out["fixed_block_half"]["graphed"] = {"ms_per_step": ms_g, "value": Bc * Tc / (ms_g * 1e-3), "roofline_5pass": roof(5 * Bc * Tc * C * 4, ms_g)}
+    except Exception as e:
+        out["fixed_block_half"]["graphed"] = {"unavailable": str(e).splitlines()[0][:200]}
     out["what"] = ("mlp_block_half: x + spectral_mix(LayerNorm(x)) fwd+bwd at the headline shape, fused prologue/epilogue vs torch LayerNorm + fused "
                    "layer + add; fixed_block_half: pre-LN causal FFT convolution + gates + residual of fft_lm's FixedSpectralBlock, fwd+bwd")
     return out

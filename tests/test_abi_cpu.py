@@ -113,3 +113,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_ext_plan_checks_without_gpu():
+    """sml_ext_supported is pure host logic (plan + window checks): callable on the CPU box."""
+    import ctypes
+    from tensor_cuda_fft_b200 import _native as native
+    lib = native.lib()
+    ok = lambda B, T, D, F, **kw: lib.sml_ext_supported(B, T, D, F, 0, ctypes.byref(native.make_ext(**kw)))
+    assert ok(16, 8192, 768, 384) == 0                                   # SpectralMLPBlock at the headline shape
+    assert ok(2, 100, 32, 16) != 0 and b"fused kernels" in lib.sml_last_error()     # generic-path shape: callers compose the unfused ops
+    assert ok(64, 2048, 512, 1024, T_in=1024, T_out=1024) == 0            # FixedSpectralBlock defaults: n_fft 2048 over 1024 rows
+    ext = native.make_ext(T_in=1024, T_out=1024)
+    ext.w_nyq = 1
+    assert lib.sml_ext_supported(64, 2048, 512, 1024, 0, ctypes.byref(ext)) == 0    # full half-spectrum: the bin T/2 is carried
+    assert lib.sml_ext_supported(16, 8192, 768, 384, 0, ctypes.byref(ext)) != 0     # band-limited plan: no bin T/2
+    assert ok(2, 2048, 64, 1024, T_in=1023, T_out=1024) != 0 and b"multiples of R" in lib.sml_last_error()
+    assert ok(2, 2048, 64, 1024, T_in=1024, T_out=512, out_row0=4) != 0 and b"out_row0" in lib.sml_last_error()
+    assert ok(2, 2048, 64, 1024, T_in=2000, in_row0=100) != 0              # window does not fit the transform
