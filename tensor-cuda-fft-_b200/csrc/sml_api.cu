@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <utility>
 
 #include "../../include/spectral_mix_b200.h"
@@ -241,7 +242,13 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
             else if (p.NR == 16) p.KJ = need <= 4 ? 4 : need <= 8 ? 8 : need <= 12 ? 12 : need <= 16 ? 16 : need <= 24 ? 24 : 32;
             else p.KJ = need <= 4 ? 4 : need <= 8 ? 8 : 16;
             if (p.NR == 16 && p.KJ == 32) p.ctas_per_sm = 2;   // 128 accumulator registers
-            if (p.NR == 32 && p.KJ >= 16) p.ctas_per_sm = 2;   // 64+ accumulator registers: 3 CTAs/SM would spill
+            // 96+ accumulator registers: two CTAs per SM.  KJ = 16 (64 accumulator registers, embed 1024: BASELINE configs[2] and
+            // the long-context sweep) still compiles to 166 registers without spills and runs 9 % faster with three CTAs per SM
+            // (cfg-3 fp32 step 1.288 -> 1.181 ms, forward 0.56 -> 0.62 of the HBM roofline; SML_FAST_CTAS=2 restores two)
+            if (p.NR == 32 && p.KJ >= 24) p.ctas_per_sm = 2;
+            // ... on most shapes: at (32, 32768, 1024) three CTAs per SM are 13 % SLOWER (the 128 KB row stride of a pass camps on
+            // DRAM channels with more rows in flight).  So this plan is tuned on first use per shape (tuned_ctas below).
+            if (p.NR == 32 && p.KJ == 16) { p.tunable = knobs().fast_ctas == 0; if (knobs().fast_ctas == 2) p.ctas_per_sm = 2; }
             if (knobs().fast_ctas == 2 && p.NR == 32 && p.KJ == 12) p.ctas_per_sm = 2;   // tuning knob: 2 or 3 CTAs per SM
             // (P = 6, i.e. 48-byte rows and 2 CTAs of 6 warps per SM, was measured at 0.320 ms per forward launch against
             //  0.197 ms for P = 4: rows that are not a multiple of the 32-byte sector straddle sectors on loads and stores.)
@@ -257,6 +264,59 @@ Plan make_plan(int T, int D, int F, int io_dtype) {
         }
     }
     return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// first-use tuning of the CTAs per SM of a tunable plan (make_plan): both variants are launched on the caller's stream (one
+// warm-up + one timed launch each, CUDA events), the faster one is cached per (device, shape, direction).  The launches write the
+// same results, so tuning is invisible except for the one-time cost; inside a CUDA-graph capture the untuned default is used.
+// ------------------------------------------------------------------------------------------------
+struct TuneKey {
+    int dev, B, T, D, F, io, bwd, grads;
+    bool operator<(const TuneKey& o) const {
+        return std::tie(dev, B, T, D, F, io, bwd, grads) < std::tie(o.dev, o.B, o.T, o.D, o.F, o.io, o.bwd, o.grads);
+    }
+};
+std::map<TuneKey, int> g_tuned;
+
+template <typename Run>
+int tuned_ctas(const TuneKey& key, const Plan& p, cudaStream_t stream, Run&& run, int* choice) {
+    *choice = p.ctas_per_sm;
+    if (!p.tunable) return 0;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_tuned.find(key);
+        if (it != g_tuned.end()) { *choice = it->second; return 0; }
+    }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) return 0;
+    cudaEvent_t e0, e1;
+    SML_CUDA(cudaEventCreate(&e0));
+    SML_CUDA(cudaEventCreate(&e1));
+    float best_ms = 0.f;
+    int best = p.ctas_per_sm;
+    for (int c = 2; c <= 3; ++c) {
+        Plan q = p;
+        q.ctas_per_sm = c;
+        float ms = 0.f;
+        int rc = run(q);                                   // warm-up (module load, shared-memory attribute, scratch)
+        for (int rep = 0; rep < 2 && !rc; ++rep) {         // best of two timed launches
+            float t = 0.f;
+            rc = cudaEventRecord(e0, stream) != cudaSuccess;
+            if (!rc) rc = run(q);
+            if (!rc) rc = cudaEventRecord(e1, stream) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess ||
+                          cudaEventElapsedTime(&t, e0, e1) != cudaSuccess;
+            if (rep == 0 || t < ms) ms = t;
+        }
+        if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc == 1 ? 1 : fail("plan tuning failed: %s", cudaGetErrorString(cudaGetLastError())); }
+        if (c == 2 || ms < best_ms) { best_ms = ms; best = c; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_tuned[key] = best;
+    *choice = best;
+    return 0;
 }
 
 // view of a (B, T, D) activation as the 4-D tensor {D, R, M, B}: t = R*m + r
@@ -319,12 +379,20 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
         prm.ntiles = B * prm.ntd;
         prm.invT = invT;
         prm.dbg = debug_record();
-        const int slots = st->sm_count * p.ctas_per_sm;
-        if (setup_split(st, p, &prm, slots, stream)) return 1;
-        const int units = prm.ntiles * prm.split;
-        const int grid = units < slots ? units : slots;
-        if (prm.split > 1) return launch_fast_split<IO, false>(p, map, map_out, prm, grid, stream);
-        return launch_fast<IO, false>(p, map, map_out, prm, grid, stream);
+        auto run = [&](const Plan& q) -> int {
+            sml::FastParams pq = prm;
+            const int slots = st->sm_count * q.ctas_per_sm;
+            if (setup_split(st, q, &pq, slots, stream)) return 1;
+            const int units = pq.ntiles * pq.split;
+            const int grid = units < slots ? units : slots;
+            if (pq.split > 1) return launch_fast_split<IO, false>(q, map, map_out, pq, grid, stream);
+            return launch_fast<IO, false>(q, map, map_out, pq, grid, stream);
+        };
+        Plan q = p;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (tuned_ctas(TuneKey{dev, B, T, D, F, io_dtype, 0, xlow != nullptr}, p, stream, run, &q.ctas_per_sm)) return 1;
+        return run(q);
     }
     // generic path
     if (p.k > 0 && xlow == nullptr) return fail("generic path needs the xlow buffer (sml_xlow_bytes) as scratch");
@@ -414,11 +482,19 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         prm.ntiles = B * prm.ntd;
         prm.invT = invT;
         prm.dbg = debug_record();
-        const int slots = st->sm_count * p.ctas_per_sm;
-        if (setup_split(st, p, &prm, slots, stream)) return 1;
-        const int units = prm.ntiles * prm.split;
-        const int grid = units < slots ? units : slots;
-        if (prm.split > 1 ? launch_fast_split<IO, true>(p, map, map_out, prm, grid, stream) : launch_fast<IO, true>(p, map, map_out, prm, grid, stream)) return 1;
+        auto run = [&](const Plan& q) -> int {
+            sml::FastParams pq = prm;
+            const int slots = st->sm_count * q.ctas_per_sm;
+            if (setup_split(st, q, &pq, slots, stream)) return 1;
+            const int units = pq.ntiles * pq.split;
+            const int grid = units < slots ? units : slots;
+            return pq.split > 1 ? launch_fast_split<IO, true>(q, map, map_out, pq, grid, stream) : launch_fast<IO, true>(q, map, map_out, pq, grid, stream);
+        };
+        Plan q = p;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (tuned_ctas(TuneKey{dev, B, T, D, F, io_dtype, 1, want_grads}, p, stream, run, &q.ctas_per_sm)) return 1;
+        if (run(q)) return 1;
         if (want_grads && launch_filtergrad_reduce(prm.gpart, prm.gbpart, gw_re, gw_im, gb, B, D, F, p.k, flat_mc, flat_next, stream)) return 1;
         return 0;
     }

@@ -16,6 +16,7 @@ struct Plan {
     int NR = 0, KJ = 0, P = 0, M = 0, R = 0;
     int ctas_per_sm = 1;
     int xb = 1;        // TMA landing tiles (2 only where the kernel variant was built with them)
+    bool tunable = false;   // CTAs per SM (2 or 3) decided by a timed first use per shape (sml_api.cu: tuned_ctas)
     bool tc = false;   // tensor-core (tcgen05) kernel of sml_tc.cuh: bf16 I/O, D % 32 == 0, T % 512 == 0, k <= 512
 };
 

@@ -61,6 +61,7 @@ int launch_fast(const Plan& p, const CUtensorMap& map_in, const CUtensorMap& map
     SML_CASE(32, 8, 4, 3)
     SML_CASE(32, 12, 4, 3)
     SML_CASE(32, 16, 4, 2)
+    SML_CASE(32, 16, 4, 3)
     SML_CASE(32, 24, 4, 2)
     SML_CASE(32, 32, 4, 2)
     SML_CASE(32, 12, 4, 2)
@@ -86,6 +87,7 @@ int launch_fast_split(const Plan& p, const CUtensorMap& map_in, const CUtensorMa
     SML_CASE(32, 8, 4, 3)
     SML_CASE(32, 12, 4, 3)
     SML_CASE(32, 16, 4, 2)
+    SML_CASE(32, 16, 4, 3)
     SML_CASE(32, 24, 4, 2)
     SML_CASE(32, 32, 4, 2)
     SML_CASE(32, 12, 4, 2)
