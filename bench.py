@@ -525,6 +525,12 @@ def run_ours(args):
             ms_g = time_steps(gstep, max(args.steps, 50), 5, barrier)
             graphed = {"ms_per_step": ms_g, "value": B * T / (ms_g * 1e-3), "unit": UNIT,
                        "what": "the same fwd+bwd step with forward and backward replayed from CUDA graphs (SpectralMixingLayer.graphed)"}
+            # the whole step (forward + backward, all gradients) as ONE graph on static buffers: one launch per step
+            replay, bufs = prob.layer.graphed_step(prob.x, prob.g)
+            ms_w = time_steps(replay, max(args.steps, 50), 5, barrier)
+            graphed["whole_step_graph"] = {"ms_per_step": ms_w, "value": B * T / (ms_w * 1e-3), "unit": UNIT,
+                                           "what": "SpectralMixingLayer.graphed_step: forward + backward captured as one CUDA graph on static buffers"}
+            del replay, bufs
         except Exception as e:
             graphed = {"unavailable": str(e).splitlines()[0][:200]}
 

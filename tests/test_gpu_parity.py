@@ -635,6 +635,27 @@ def test_cuda_graph_capture(pkg, dev):
         assert torch.equal(a, b.detach())      # same kernels, same inputs: bit-identical (the gradient sum is deterministic)
 
 
+def test_graphed_step_whole_graph(pkg, dev):
+    """SpectralMixingLayer.graphed_step: forward + backward as ONE graph on static buffers; replays with new inputs match eager."""
+    B, T, D = 8, 512, 256                     # BASELINE configs[0]
+    gen = torch.Generator().manual_seed(12)
+    layer = make_layer(pkg, D, D // 2, torch.randn(D, D // 2, generator=gen), torch.randn(D, D // 2, generator=gen),
+                       torch.randn(D, generator=gen), dev)
+    x0, g0 = torch.randn(B, T, D, generator=gen).to(dev), torch.randn(B, T, D, generator=gen).to(dev)
+    replay, bufs = layer.graphed_step(x0, g0)
+    for seed in (1, 2):
+        gen2 = torch.Generator().manual_seed(seed)
+        x, g = torch.randn(B, T, D, generator=gen2).to(dev), torch.randn(B, T, D, generator=gen2).to(dev)
+        bufs["x"].copy_(x)
+        bufs["g"].copy_(g)
+        replay()
+        got = [bufs["y"].clone(), bufs["gx"].clone(), layer.weight_real.grad.clone(), layer.weight_imag.grad.clone(), layer.bias.grad.clone()]
+        ref = make_layer(pkg, D, D // 2, layer.weight_real.detach().cpu(), layer.weight_imag.detach().cpu(), layer.bias.detach().cpu(), dev)
+        want = run_layer(ref, x.cpu(), g.cpu(), dev)
+        for name, a, b in zip(NAMES, got, want):
+            assert orc.rel_l2(a.float().cpu().numpy(), b) <= 1e-6, (seed, name)
+
+
 def test_random_stress_vs_torch_fft():
     # 120 random (B, T, D, F, dtype) problems across every plan family against the reference algorithm (torch.fft + autograd)
     # on the same GPU -- tools/stress.py exits non-zero on the first mismatch
