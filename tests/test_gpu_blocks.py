@@ -283,3 +283,67 @@ def test_ext_row_windows(pkg, dev):
         torch.cuda.synchronize()
         assert rel_l2(out.cpu().numpy(), want.numpy()) <= 1e-5, (T_in, in0, T_out, out0)
         assert rel_l2(xnyq.cpu().numpy(), X[:, Fn, :].real.numpy()) <= 1e-5
+
+
+def test_blocks_random_shapes(pkg, dev):
+    """Randomised shapes over every plan family the extended kernels take (sub-transform 64 / 256 / 1024, R = 1 .. 16, wide-band
+    forms, fp32 and bf16): the fused SpectralMLPBlock half against the unfused composition, FixedSpectralBlock's half against
+    the oracle restatement of the reference lines."""
+    from tensor_cuda_fft_b200 import spectral_conv as sc
+    from tensor_cuda_fft_b200 import spectral_layers as sl
+    rng = np.random.default_rng(2024)
+    n_fused = 0
+    for case in range(40):
+        T = int(rng.choice([64, 128, 192, 256, 512, 768, 1024, 2048, 3072, 4096]))
+        D = int(rng.choice([8, 16, 24, 40, 64, 96, 136, 256]))
+        B = int(rng.integers(1, 4))
+        nf = int(rng.choice([max(1, D // 2), 5, 33, 100, 300]))
+        dtype = torch.float32 if rng.random() < 0.7 else torch.bfloat16
+        torch.manual_seed(case)
+        norm = torch.nn.LayerNorm(D).to(dev)
+        layer = pkg.SpectralMixingLayer(D, num_filters=nf).to(dev)
+        with torch.no_grad():
+            for p in list(norm.parameters()) + list(layer.parameters()):
+                p.add_(0.5 * torch.randn_like(p))
+        x = (torch.randn(B, T, D) * 1.5 + 0.3).to(dev, dtype)
+        g = torch.randn(B, T, D).to(dev, dtype)
+        xa = x.clone().requires_grad_(True)
+        if not sl.fused_block_supported(xa, norm, layer):
+            continue
+        n_fused += 1
+        ya = sl.ln_spectral_mix_residual(xa, norm, layer)
+        ya.backward(g)
+        ga = [xa.grad] + [p.grad.clone() for p in list(norm.parameters()) + list(layer.parameters())]
+        for p in list(norm.parameters()) + list(layer.parameters()):
+            p.grad = None
+        xb = x.float().clone().requires_grad_(True)
+        yb = xb + layer(norm(xb))
+        yb.backward(g.float())
+        gb = [xb.grad] + [p.grad.clone() for p in list(norm.parameters()) + list(layer.parameters())]
+        tol = 2e-5 if dtype == torch.float32 else 2e-2
+        tag = (case, B, T, D, nf, str(dtype))
+        assert rel_l2(ya.detach().float().cpu().numpy(), yb.detach().cpu().numpy()) <= tol, tag
+        for i, (a, b) in enumerate(zip(ga, gb)):
+            if float(b.float().abs().max()) > 0:
+                assert rel_l2(a.float().cpu().numpy(), b.float().cpu().numpy()) <= 5 * tol, tag + (i,)
+    assert n_fused >= 20
+    for case in range(12):
+        T = int(rng.choice([32, 48, 64, 100, 128, 200, 256, 500, 1024]))
+        K = int(rng.choice([4, 8, 16, 32, 64]))
+        C = int(rng.choice([8, 16, 32, 48]))
+        B = int(rng.integers(1, 4))
+        x = torch.randn(B, T, C)
+        if not sc.causal_spectral_conv_supported(x.to(dev), K):
+            continue
+        torch.manual_seed(100 + case)
+        blk = sc.FixedSpectralBlock(C, seq_len=T, kernel_len=K, transition_bins=4, dropout=0.0)
+        with torch.no_grad():
+            for p in blk.parameters():
+                p.add_(0.2 * torch.randn_like(p))
+            blk.kernel.copy_(0.2 * torch.randn(K))
+        sd = {k: v.clone() for k, v in blk.state_dict().items()}
+        cutoff = None if case % 3 else int(rng.integers(2, sc.conv_fft_len(T, K) // 2))
+        want = bo.fixed_block_spectral_half(x, sd["ln.weight"], sd["ln.bias"], 1e-5, sd["kernel"], sd["gain"], sd["gate_freq_logits"],
+                                            sd["gate_ctx.weight"], sd["gate_ctx.bias"], cutoff=cutoff, transition_bins=4)
+        got = blk.to(dev).eval().spectral_half(x.to(dev), cutoff)
+        assert rel_l2(got.detach().cpu().numpy(), want.numpy()) <= 2e-5, (case, B, T, K, C, cutoff)
