@@ -293,24 +293,30 @@ int tuned_ctas(const TuneKey& key, const Plan& p, cudaStream_t stream, Run&& run
     cudaEvent_t e0, e1;
     SML_CUDA(cudaEventCreate(&e0));
     SML_CUDA(cudaEventCreate(&e1));
-    float best_ms = 0.f;
-    int best = p.ctas_per_sm;
-    for (int c = 2; c <= 3; ++c) {
+    // warm both variants (module load, shared-memory attribute, scratch, TLB), then three alternating timed rounds, minimum each
+    float ms[2] = {0.f, 0.f};
+    int rc = 0;
+    for (int c = 2; c <= 3 && !rc; ++c) {
         Plan q = p;
         q.ctas_per_sm = c;
-        float ms = 0.f;
-        int rc = run(q);                                   // warm-up (module load, shared-memory attribute, scratch)
-        for (int rep = 0; rep < 2 && !rc; ++rep) {         // best of two timed launches
+        rc = run(q);
+    }
+    for (int round = 0; round < 3 && !rc; ++round)
+        for (int c = 2; c <= 3 && !rc; ++c) {
+            Plan q = p;
+            q.ctas_per_sm = c;
             float t = 0.f;
             rc = cudaEventRecord(e0, stream) != cudaSuccess;
             if (!rc) rc = run(q);
             if (!rc) rc = cudaEventRecord(e1, stream) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess ||
                           cudaEventElapsedTime(&t, e0, e1) != cudaSuccess;
-            if (rep == 0 || t < ms) ms = t;
+            if (round == 0 || t < ms[c - 2]) ms[c - 2] = t;
         }
-        if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc == 1 ? 1 : fail("plan tuning failed: %s", cudaGetErrorString(cudaGetLastError())); }
-        if (c == 2 || ms < best_ms) { best_ms = ms; best = c; }
-    }
+    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc == 1 ? 1 : fail("plan tuning failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    const int best = ms[1] < ms[0] ? 3 : 2;
+    if (getenv("SML_TUNE_VERBOSE"))
+        fprintf(stderr, "[sml tune] B=%d T=%d D=%d F=%d io=%d bwd=%d grads=%d: 2 CTAs/SM %.4f ms, 3 CTAs/SM %.4f ms -> %d\n", key.B, key.T, key.D,
+                key.F, key.io, key.bwd, key.grads, ms[0], ms[1], best);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     std::lock_guard<std::mutex> lk(g_mu);
