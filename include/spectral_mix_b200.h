@@ -143,6 +143,11 @@ typedef struct sml_ext {
     const float* sb_nyq;      /*   Forward only; all three or none (sb_nyq only with w_nyq).                                   */
     float* x_nyq;             /* (B, D): spectrum at the bin T/2; written by the forward, read by the backward */
     float* g_nyq;             /* (B, D): backward only: per-batch-element gradient terms of w_nyq (sum over B outside) */
+    float* d_core;            /* (B, D): backward only: (1/T) sum_f Re(conj(G) X W) incl. the bin T/2 -- with d_q the gradient of      */
+    float* d_q;               /*   chan_scale without a pass over y: dL/dchan_scale[b,c] = d_core + bg[c] * d_q for sb = bg[c] * Q[f]; */
+    const float* q_re;        /*   d_q[b,c] = (1/T) sum_f Re(conj(G) Q), Q = (q_re, q_im) of shape (F,), q_nyq its bin T/2.            */
+    const float* q_im;        /*   Needs xlow.  All nullable.                                                                        */
+    const float* q_nyq;       /*   (1,) device scalar                                                                                */
     int T_in, in_row0;        /* x holds T_in rows; x row i is transform row in_row0 + i; the other transform rows are zero */
     int T_out, out_row0;      /* y holds T_out rows = transform rows 0 .. T_out-1, the rest is dropped.  out_row0 must be 0 (TMA
                                  stores cannot start at a negative coordinate): an output window starting at row o is the phase

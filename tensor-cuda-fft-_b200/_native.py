@@ -43,15 +43,17 @@ class SmlExt(ctypes.Structure):
     _fields_ = [("row_stats", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("chan_scale", ctypes.c_void_p),
                 ("w_nyq", ctypes.c_void_p), ("sb_re", ctypes.c_void_p), ("sb_im", ctypes.c_void_p), ("sb_nyq", ctypes.c_void_p),
                 ("x_nyq", ctypes.c_void_p), ("g_nyq", ctypes.c_void_p),
+                ("d_core", ctypes.c_void_p), ("d_q", ctypes.c_void_p), ("q_re", ctypes.c_void_p), ("q_im", ctypes.c_void_p),
+                ("q_nyq", ctypes.c_void_p),
                 ("T_in", ctypes.c_int), ("in_row0", ctypes.c_int), ("T_out", ctypes.c_int), ("out_row0", ctypes.c_int)]
 
 
 def make_ext(row_stats=None, residual=None, chan_scale=None, w_nyq=None, sb_re=None, sb_im=None, sb_nyq=None, x_nyq=None,
-             g_nyq=None, T_in=0, in_row0=0, T_out=0, out_row0=0) -> SmlExt:
+             g_nyq=None, T_in=0, in_row0=0, T_out=0, out_row0=0, d_core=None, d_q=None, q_re=None, q_im=None, q_nyq=None) -> SmlExt:
     """Build an ``sml_ext`` from torch tensors (or None).  The caller keeps the tensors alive for the duration of the call."""
     p = lambda t: None if t is None else t.data_ptr()
     return SmlExt(p(row_stats), p(residual), p(chan_scale), p(w_nyq), p(sb_re), p(sb_im), p(sb_nyq), p(x_nyq), p(g_nyq),
-                  int(T_in), int(in_row0), int(T_out), int(out_row0))
+                  p(d_core), p(d_q), p(q_re), p(q_im), p(q_nyq), int(T_in), int(in_row0), int(T_out), int(out_row0))
 
 
 def _declare(lib):

@@ -619,6 +619,13 @@ int ext_impl(const void* in, const float* w_re, const float* w_im, const float* 
     if (prm.sb_re != nullptr && prm.sb_im == nullptr) return fail("sb_re and sb_im must be given together");
     prm.xnyq = e ? e->x_nyq : nullptr;
     prm.gnyqpart = (BWD && e) ? e->g_nyq : nullptr;
+    prm.d_core = (BWD && e) ? e->d_core : nullptr;
+    prm.d_q = (BWD && e && e->q_re && e->q_im) ? e->d_q : nullptr;
+    prm.q_re = (BWD && e) ? e->q_re : nullptr;
+    prm.q_im = (BWD && e) ? e->q_im : nullptr;
+    prm.q_nyq = (BWD && e) ? e->q_nyq : nullptr;
+    if (prm.d_core != nullptr && xlow == nullptr) return fail("d_core needs xlow saved by sml_forward_ext");
+    if (prm.q_re != nullptr && prm.q_im == nullptr) prm.q_re = nullptr;
     prm.res = res ? 1 : 0;
     if (row0_out != 0) return fail("the backward of a problem with in_row0 != 0 is not supported (its output rows would start at a shifted row)");
     prm.in_q = row0_in / p.R; prm.in_r = row0_in % p.R;

@@ -66,6 +66,13 @@ struct FastParams {
     const float* wnyq;     // (D,) real weight of the bin T/2 (full half-spectrum filters, irfft semantics), or null
     float* xnyq;           // (B, D) spectrum at the bin T/2 (real): written by FWD, read by BWD
     float* gnyqpart;       // (B, D) per-batch-element gradient terms of wnyq, written by BWD
+    // BWD: gradient of the per-(b, c) factor from the spectra the mid phase holds anyway (no pass over y):
+    //   d_core[b,c] = (1/T) sum_f Re(conj(G_f) X_f W_f) (+ bin T/2),  d_q[b,c] = (1/T) sum_f Re(conj(G_f) Q_f)  -- dL/dscale = d_core + bg[c] d_q
+    float* d_core;         // (B, D) or null
+    float* d_q;            // (B, D) or null (needs q_re / q_im)
+    const float* q_re;     // (F,) rank-one spectral bias: sb[c,f] = bg[c] * Q[f]
+    const float* q_im;
+    const float* q_nyq;    // (1,) its bin T/2 (device scalar), or null
     int res;               // 1: tmap_res describes a residual tensor (output geometry) that is added to the output rows
     int in_q, in_r;        // input row i is transform row in_row0 + i, in_row0 = R * in_q + in_r (rows outside the input read as
                            // zero); output row i is transform row i (rows past the output tensor are not written)
@@ -262,6 +269,8 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
     const int D = prm.D;
     const bool pvalid = d0 < D;
     const bool grads = BWD && prm.gw_re != nullptr && side;
+    const bool want_ds = EXT && BWD && prm.d_core != nullptr && side;   // needs X_low like the filter gradient
+    float ec0 = 0.f, ec1 = 0.f, eq0 = 0.f, eq1 = 0.f;
     // EXT: per-(batch element, channel) factor on the filtered spectrum, and the raw analysis value of the bin -T/2
     float sc0 = 1.f, sc1 = 1.f;
     cf znyq = cf{0.f, 0.f};
@@ -298,7 +307,7 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
                 wv[jj][1] = __ldg(prm.w_im + wrow0 + af);
                 wv[jj][2] = __ldg(prm.w_re + wrow1 + af);
                 wv[jj][3] = __ldg(prm.w_im + wrow1 + af);
-                if (grads) {
+                if (grads || want_ds) {
                     xv[jj][0] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
                     xv[jj][1] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
                 }
@@ -322,7 +331,18 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
             cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
             const cf w0 = cf{wv[jj][0], wv[jj][1]}, w1 = cf{wv[jj][2], wv[jj][3]};
             const float gdc0 = s0.re, gdc1 = s1.re;   // BWD: sum_t g of the two channels when af == 0 (before any scaling)
-            if constexpr (EXT && BWD) {   // y = scale * ifft(W X): the gradient entering the filter is scale * G
+            if constexpr (EXT && BWD) {
+                if (want_ds && live) {   // dL/dscale terms of this bin, from the unscaled G
+                    const cf A0 = cmul(cf{xv[jj][0].x, xv[jj][0].y}, w0), A1 = cmul(cf{xv[jj][1].x, xv[jj][1].y}, w1);
+                    ec0 = fmaf(s0.re, A0.re, fmaf(s0.im, A0.im, ec0));
+                    ec1 = fmaf(s1.re, A1.re, fmaf(s1.im, A1.im, ec1));
+                    if (prm.q_re != nullptr) {
+                        const float qr = __ldg(prm.q_re + af), qi = __ldg(prm.q_im + af);
+                        eq0 = fmaf(s0.re, qr, fmaf(s0.im, qi, eq0));
+                        eq1 = fmaf(s1.re, qr, fmaf(s1.im, qi, eq1));
+                    }
+                }
+                // y = scale * ifft(W X): the gradient entering the filter is scale * G
                 s0 = cf{s0.re * sc0, s0.im * sc0};
                 s1 = cf{s1.re * sc1, s1.im * sc1};
             }
@@ -379,6 +399,30 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
 #pragma unroll
         for (int idx = NJ - 1; idx > KJ; --idx) acc[idx] = acc[idx - 1];
         acc[KJ] = cf{0.f, 0.f};
+    }
+    if constexpr (EXT && BWD) {
+        if (prm.d_core != nullptr) {   // (uniform branch: every lane takes part in the shuffles)
+#pragma unroll
+            for (int o = NR / 2; o > 0; o >>= 1) {   // sum over the NR lanes (f1) that share this channel pair
+                ec0 += __shfl_xor_sync(0xffffffffu, ec0, o);
+                ec1 += __shfl_xor_sync(0xffffffffu, ec1, o);
+                eq0 += __shfl_xor_sync(0xffffffffu, eq0, o);
+                eq1 += __shfl_xor_sync(0xffffffffu, eq1, o);
+            }
+            if (want_ds && ff1 == 0 && pvalid) {
+                const size_t o = (size_t)b * D + d0;
+                if (prm.wnyq != nullptr && prm.xnyq != nullptr) {   // bin T/2: G and X real there
+                    ec0 = fmaf(znyq.re, prm.xnyq[o] * __ldg(prm.wnyq + d0), ec0);
+                    ec1 = fmaf(znyq.im, prm.xnyq[o + 1] * __ldg(prm.wnyq + d0 + 1), ec1);
+                    const float qn = prm.q_nyq != nullptr ? __ldg(prm.q_nyq) : 0.f;
+                    eq0 = fmaf(znyq.re, qn, eq0);
+                    eq1 = fmaf(znyq.im, qn, eq1);
+                }
+                prm.d_core[o] = ec0 * prm.invT;
+                prm.d_core[o + 1] = ec1 * prm.invT;
+                if (prm.d_q != nullptr) { prm.d_q[o] = eq0 * prm.invT; prm.d_q[o + 1] = eq1 * prm.invT; }
+            }
+        }
     }
     if constexpr (EXT) {
         // bin T/2 (== -T/2): Z = X_d + i X_{d+1} with both spectra real there; irfft semantics: weight 1/T, real filter weight

@@ -82,7 +82,9 @@ class _CausalSpectralConvFn(torch.autograd.Function):
         sb_im = (bg[:, None] * q_im.detach().float()[None, :]).contiguous()
         sb_nyq = (bg * q_nyq.detach().float()).contiguous()
         y = torch.empty_like(xc)
-        need_filter_grad = any(ctx.needs_input_grad[1:4])
+        # the saved spectrum serves the filter gradient AND the gate gradient (d_core, which also feeds dL/dx through the pooled
+        # context): needed whenever anything is differentiated
+        need_filter_grad = any(ctx.needs_input_grad)
         xlow = torch.empty(max(_shape_info(B, n_fft, C, Fn, io)[1] // 8, 1), dtype=torch.complex64, device=dev) if need_filter_grad else None
         xnyq = torch.empty(B, C, dtype=torch.float32, device=dev)
         ext = _native.make_ext(row_stats=stats, residual=xc if add_residual else None, chan_scale=s, w_nyq=wn, sb_re=sb_re,
@@ -90,14 +92,15 @@ class _CausalSpectralConvFn(torch.autograd.Function):
         with _on_device(dev):
             _native.check(lib.sml_forward_ext(_ptr(xc), _ptr(wr), _ptr(wi), None, _ptr(y), _ptr(xlow), B, n_fft, C, Fn, io,
                                               ctypes.byref(ext), _stream_handle(dev)))
-        ctx.save_for_backward(xc, y, stats, wr, wi, wn, xlow, xnyq, s, pooled, mhat, beta_gain, u, gamma, gate_w)
+        qr, qi, qn = _f32c(q_re), _f32c(q_im), _f32c(q_nyq).reshape(1)
+        ctx.save_for_backward(xc, stats, wr, wi, wn, xlow, xnyq, s, pooled, mhat, beta_gain, gamma, gate_w, qr, qi, qn)
         ctx.cfg = (B, T, C, Fn, io, n_fft, add_residual)
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        xc, y, stats, wr, wi, wn, xlow, xnyq, s, pooled, mhat, beta_gain, u, gamma, gate_w = ctx.saved_tensors
+        xc, stats, wr, wi, wn, xlow, xnyq, s, pooled, mhat, beta_gain, gamma, gate_w, qr, qi, qn = ctx.saved_tensors
         B, T, C, Fn, io, n_fft, add_residual = ctx.cfg
         lib = _native.lib()
         dev = g.device
@@ -112,14 +115,18 @@ class _CausalSpectralConvFn(torch.autograd.Function):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         gnyq = torch.empty(B, C, dtype=torch.float32, device=dev)
         gh = torch.empty_like(gc)
-        ext = _native.make_ext(chan_scale=s, w_nyq=wn, x_nyq=xnyq, g_nyq=gnyq, T_in=T, T_out=T)
+        d_core = torch.empty(B, C, dtype=torch.float32, device=dev)
+        d_q = torch.empty(B, C, dtype=torch.float32, device=dev)
+        ext = _native.make_ext(chan_scale=s, w_nyq=wn, x_nyq=xnyq, g_nyq=gnyq, T_in=T, T_out=T, d_core=d_core, d_q=d_q, q_re=qr, q_im=qi,
+                               q_nyq=qn)
         with _on_device(dev):
             _native.check(lib.sml_backward_ext(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gh), _ptr(gwr), _ptr(gwi), _ptr(gb),
                                                _ptr(ws), ws_bytes, B, n_fft, C, Fn, io, ctypes.byref(ext), _stream_handle(dev)))
-        gf = gc.float()
-        # gate: y - residual = s * core  =>  ds = sum_t g * core = sum_t g * (y - residual) / s   (s = sigmoid(.) > 0)
-        core_s = (y.float() - xc.float()) if add_residual else y.float()
-        ds = (gf * core_s).sum(1) / s
+        # gate: dL/ds[b,c] = sum_t g * (y - residual) / s, evaluated by the backward kernel in the spectral domain (it holds G, X_low and
+        # the filter anyway): (1/T) sum_f Re(conj(G) (X W + beta_gain[c] Q)) = d_core + beta_gain[c] * d_q -- no pass over y, and y
+        # is not kept for the backward
+        bgf = beta_gain.float()
+        ds = d_core + bgf * d_q
         dz = ds * s * (1.0 - s)
         d_gate_w = dz.t() @ pooled
         d_gate_b = dz.sum(0)
@@ -128,11 +135,9 @@ class _CausalSpectralConvFn(torch.autograd.Function):
         d_beta = dpooled.sum(0)
         dmhat = dpooled * gamma.float()                       # d/d(mean_t x^): spreads over the T rows as dmhat / T
         # beta path: y_beta[b,t,c] = s[b,c] * beta_gain[c] * u[t]
-        # two batched matrix-vector products over g (one read each) instead of a (T, C) intermediate:
-        #   d_beta_gain[c] = sum_b s[b,c] * (u^T g[b])[c] ;  d_u[t] = sum_b (g[b] (s[b] * beta_gain))[t]
-        ug = torch.matmul(u.to(gc.dtype), gc).float()                                   # (B, C)
-        d_beta_gain = (ug * s).sum(0)
-        d_u = torch.bmm(gc, (s * beta_gain.float()).to(gc.dtype).unsqueeze(2)).squeeze(2).float().sum(0)
+        #   d_beta_gain[c] = sum_b s[b,c] * d_q[b,c] ;  d_u[t] = sum_b (g[b] (s[b] * beta_gain))[t]  (one batched matrix-vector product over g)
+        d_beta_gain = (s * d_q).sum(0)
+        d_u = torch.bmm(gc, (s * bgf).to(gc.dtype).unsqueeze(2)).squeeze(2).float().sum(0)
         # LayerNorm backward (+ the skip connection's gradient, + the pooled-mean term) in one pass
         # (the pooled-mean term enters dL/dx^ as the per-(b, c) constant dmhat / T: chan_add of the same kernel)
         chan_add = (dmhat / T).contiguous()
