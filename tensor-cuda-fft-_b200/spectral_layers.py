@@ -274,6 +274,10 @@ def fused_block_supported(x: torch.Tensor, norm: nn.LayerNorm, layer: "SpectralM
         return False
     if layer.training and layer.dropout.p > 0.0:      # dropout sits between the layer and the skip connection (:118, :185)
         return False
+    if getattr(layer, "_grad_bucket", None) is not None:
+        # data-parallel job with the fused reduce + all-reduce (distributed.attach_symmetric_grad_buffers): the filter gradients must
+        # leave through the layer's own backward (sml_backward_allreduce), which the block-level function does not call
+        return False
     B, T, D = x.shape
     return _ext_supported(B, T, D, layer.weight_real.shape[1], _IO_DTYPES[x.dtype])
 
