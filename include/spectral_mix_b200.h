@@ -148,6 +148,18 @@ typedef struct sml_ext {
     const float* q_re;        /*   d_q[b,c] = (1/T) sum_f Re(conj(G) Q), Q = (q_re, q_im) of shape (F,), q_nyq its bin T/2.            */
     const float* q_im;        /*   Needs xlow.  All nullable.                                                                        */
     const float* q_nyq;       /*   (1,) device scalar                                                                                */
+    /* Rank-one filter mode (h_re != NULL; w_re / w_im of the call may then be NULL): w[d,f] = chan[d] * (h_re, h_im)[f] and, in the
+     * forward, sb[d,f] = bg[d] * (q_re, q_im)[f] are formed inside the kernel -- the multiplier of FixedSpectralBlock is
+     * gain[c] * H[f], there is no (D, F) array to read.  w_nyq / sb_nyq stay (D,) vectors.  Backward: the filter gradient is
+     * contracted over the channels in the kernel, hpart[item, f] = sum_{c in item} chan[c] gW[b,c,f] with items = B * ceil(D / 2P)
+     * rows of k complex bins (sum the rows for dL/dH; sml_ext_hpart_rows gives the row count) -- no (B, D, k) spill, no workspace;
+     * d_core is then taken against H instead of W: dL/dchan[c] = sum_b chan_scale * d_core, dL/dchan_scale = chan * d_core + bg * d_q. */
+    const float* h_re;        /* (F,) */
+    const float* h_im;        /* (F,) */
+    const float* h_nyq;       /* (1,) device scalar: H at the bin T/2 (real), for d_core */
+    const float* chan;        /* (D,) */
+    const float* bg;          /* (D,) or NULL */
+    void* hpart;              /* (sml_ext_hpart_rows, k) complex64, backward only */
     int T_in, in_row0;        /* x holds T_in rows; x row i is transform row in_row0 + i; the other transform rows are zero */
     int T_out, out_row0;      /* y holds T_out rows = transform rows 0 .. T_out-1, the rest is dropped.  out_row0 must be 0 (TMA
                                  stores cannot start at a negative coordinate): an output window starting at row o is the phase
@@ -158,6 +170,9 @@ typedef struct sml_ext {
 /* 0 if sml_forward_ext / sml_backward_ext can run this problem (fused plan, row windows compatible with it); else an error
  * with the reason in sml_last_error(). */
 int sml_ext_supported(int B, int T, int D, int F, int io_dtype, const sml_ext* ext);
+
+/* Rows of sml_ext.hpart for a problem (work items of the fused plan: B * channel tiles); 0 if the plan is not fused. */
+int sml_ext_hpart_rows(int B, int T, int D, int F, int io_dtype);
 
 /* sml_forward / sml_backward with the extensions above.  xlow then holds the spectrum of the normalised, zero-padded
  * input; gw_re / gw_im / gb are the gradients of the arrays that were passed in (the host maps them back onto the block's

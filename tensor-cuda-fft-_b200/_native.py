@@ -45,15 +45,17 @@ class SmlExt(ctypes.Structure):
                 ("x_nyq", ctypes.c_void_p), ("g_nyq", ctypes.c_void_p),
                 ("d_core", ctypes.c_void_p), ("d_q", ctypes.c_void_p), ("q_re", ctypes.c_void_p), ("q_im", ctypes.c_void_p),
                 ("q_nyq", ctypes.c_void_p),
+                ("h_re", ctypes.c_void_p), ("h_im", ctypes.c_void_p), ("h_nyq", ctypes.c_void_p), ("chan", ctypes.c_void_p),
+                ("bg", ctypes.c_void_p), ("hpart", ctypes.c_void_p),
                 ("T_in", ctypes.c_int), ("in_row0", ctypes.c_int), ("T_out", ctypes.c_int), ("out_row0", ctypes.c_int)]
 
 
 def make_ext(row_stats=None, residual=None, chan_scale=None, w_nyq=None, sb_re=None, sb_im=None, sb_nyq=None, x_nyq=None,
-             g_nyq=None, T_in=0, in_row0=0, T_out=0, out_row0=0, d_core=None, d_q=None, q_re=None, q_im=None, q_nyq=None) -> SmlExt:
+             g_nyq=None, T_in=0, in_row0=0, T_out=0, out_row0=0, d_core=None, d_q=None, q_re=None, q_im=None, q_nyq=None, h_re=None, h_im=None, h_nyq=None, chan=None, bg=None, hpart=None) -> SmlExt:
     """Build an ``sml_ext`` from torch tensors (or None).  The caller keeps the tensors alive for the duration of the call."""
     p = lambda t: None if t is None else t.data_ptr()
     return SmlExt(p(row_stats), p(residual), p(chan_scale), p(w_nyq), p(sb_re), p(sb_im), p(sb_nyq), p(x_nyq), p(g_nyq),
-                  p(d_core), p(d_q), p(q_re), p(q_im), p(q_nyq), int(T_in), int(in_row0), int(T_out), int(out_row0))
+                  p(d_core), p(d_q), p(q_re), p(q_im), p(q_nyq), p(h_re), p(h_im), p(h_nyq), p(chan), p(bg), p(hpart), int(T_in), int(in_row0), int(T_out), int(out_row0))
 
 
 def _declare(lib):
@@ -94,6 +96,8 @@ def _declare(lib):
     lib.sml_wirtinger_filter_backward.restype = c_int
     lib.sml_wirtinger_filter_backward.argtypes = [c_void_p] * 7 + [c_int] * 4 + [c_void_p]
     ext_p = ctypes.POINTER(SmlExt)
+    lib.sml_ext_hpart_rows.restype = c_int
+    lib.sml_ext_hpart_rows.argtypes = [c_int] * 5
     lib.sml_ext_supported.restype = c_int
     lib.sml_ext_supported.argtypes = [c_int] * 5 + [ext_p]
     lib.sml_forward_ext.restype = c_int
@@ -114,7 +118,7 @@ EXPORTED_SYMBOLS = (
     "sml_wirtinger_mul_forward", "sml_wirtinger_mul_backward",
     "sml_wirtinger_filter_forward", "sml_wirtinger_filter_backward",
     "sml_launch_count", "sml_debug_dump", "sml_release", "sml_backward_allreduce",
-    "sml_ext_supported", "sml_forward_ext", "sml_backward_ext", "sml_ln_stats", "sml_ln_backward", "sml_spectral_ema_scan",
+    "sml_ext_supported", "sml_ext_hpart_rows", "sml_forward_ext", "sml_backward_ext", "sml_ln_stats", "sml_ln_backward", "sml_spectral_ema_scan",
 )
 
 

@@ -621,9 +621,18 @@ int ext_impl(const void* in, const float* w_re, const float* w_im, const float* 
     prm.gnyqpart = (BWD && e) ? e->g_nyq : nullptr;
     prm.d_core = (BWD && e) ? e->d_core : nullptr;
     prm.d_q = (BWD && e && e->q_re && e->q_im) ? e->d_q : nullptr;
-    prm.q_re = (BWD && e) ? e->q_re : nullptr;
-    prm.q_im = (BWD && e) ? e->q_im : nullptr;
-    prm.q_nyq = (BWD && e) ? e->q_nyq : nullptr;
+    prm.q_re = e ? e->q_re : nullptr;
+    prm.q_im = e ? e->q_im : nullptr;
+    prm.q_nyq = e ? e->q_nyq : nullptr;
+    if (e && e->h_re != nullptr) {   // rank-one filter mode
+        if (e->h_im == nullptr || e->chan == nullptr) return fail("rank-one filter mode needs h_re, h_im and chan");
+        prm.h_re = e->h_re; prm.h_im = e->h_im; prm.h_nyq = e->h_nyq; prm.chan = e->chan; prm.bg = e->bg;
+        prm.hpart = BWD ? reinterpret_cast<sml::cf*>(e->hpart) : nullptr;
+        if (prm.hpart != nullptr && xlow == nullptr) return fail("hpart needs xlow saved by sml_forward_ext");
+        if (want_grads) return fail("rank-one filter mode returns the filter gradient through hpart: pass gw_re = gw_im = gb = NULL");
+    } else if (w_re == nullptr || w_im == nullptr) {
+        return fail("null filter pointer");
+    }
     if (prm.d_core != nullptr && xlow == nullptr) return fail("d_core needs xlow saved by sml_forward_ext");
     if (prm.q_re != nullptr && prm.q_im == nullptr) prm.q_re = nullptr;
     prm.res = res ? 1 : 0;
@@ -973,10 +982,15 @@ int sml_ext_supported(int B, int T, int D, int F, int io_dtype, const sml_ext* e
     return ext_check(p, T, D, ext, &g);
 }
 
+int sml_ext_hpart_rows(int B, int T, int D, int F, int io_dtype) {
+    const Plan p = make_plan_ext(T, D, F, io_dtype);
+    if (p.path != SML_PATH_FAST || B < 1) return 0;
+    return B * ((D + 2 * p.P - 1) / (2 * p.P));
+}
+
 int sml_forward_ext(const void* x, const float* w_re, const float* w_im, const float* bias, void* y, void* xlow_save, int B,
                     int T, int D, int F, int io_dtype, const sml_ext* ext, void* stream) {
     if (check_common(x, y, B, T, D, F, io_dtype)) return 1;
-    if (w_re == nullptr || w_im == nullptr) return fail("null filter pointer");
     g_err[0] = 0;
     if (io_dtype == SML_DTYPE_F32)
         return ext_impl<float, false>(x, w_re, w_im, bias, y, xlow_save, nullptr, nullptr, nullptr, nullptr, 0, B, T, D, F, io_dtype, ext,
@@ -989,7 +1003,6 @@ int sml_backward_ext(const void* g, const void* xlow, const float* w_re, const f
                      float* gb, void* workspace, size_t workspace_bytes, int B, int T, int D, int F, int io_dtype,
                      const sml_ext* ext, void* stream) {
     if (check_common(g, gx, B, T, D, F, io_dtype)) return 1;
-    if (w_re == nullptr || w_im == nullptr) return fail("null filter pointer");
     g_err[0] = 0;
     if (io_dtype == SML_DTYPE_F32)
         return ext_impl<float, true>(g, w_re, w_im, nullptr, gx, const_cast<void*>(xlow), gw_re, gw_im, gb, workspace, workspace_bytes, B,

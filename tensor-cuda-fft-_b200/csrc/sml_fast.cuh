@@ -73,6 +73,17 @@ struct FastParams {
     const float* q_re;     // (F,) rank-one spectral bias: sb[c,f] = bg[c] * Q[f]
     const float* q_im;
     const float* q_nyq;    // (1,) its bin T/2 (device scalar), or null
+    // rank-one filter mode (h_re != null): w[d,f] = chan[d] * H[f] (and sb[d,f] = bg[d] * Q[f], FWD) are formed in the mid phase
+    // from two (F,) arrays and two (D,) vectors instead of being read as (D, F) arrays; in BWD the filter gradient is contracted
+    // over the channels in the kernel: hpart[item, f] = sum_{c in item} chan[c] (1/T) scale G conj(X)  (k complex per work item,
+    // summed over the items by the host) -- no (B, D, k) spill -- and d_core is evaluated with H instead of W (dL/dchan = sum_b
+    // scale * d_core, dL/dscale = chan * d_core + bg * d_q).  The FastCfg exchange buffer carries the sum over the P channel pairs.
+    const float* h_re;
+    const float* h_im;
+    const float* h_nyq;    // (1,) H at the bin T/2 (real)
+    const float* chan;     // (D,)
+    const float* bg;       // (D,) or null
+    cf* hpart;             // (ntiles, k), BWD
     int res;               // 1: tmap_res describes a residual tensor (output geometry) that is added to the output rows
     int in_q, in_r;        // input row i is transform row in_row0 + i, in_row0 = R * in_q + in_r (rows outside the input read as
                            // zero); output row i is transform row i (rows past the output tensor are not written)
@@ -263,12 +274,23 @@ __device__ __forceinline__ void prefetch_xlow_l2(const FastParams& prm, int b, i
 // ------------------------------------------------------------------------------------------------
 // side = false (pass splitting: every CTA of a group runs the mid phase on the same summed band): skip the global side outputs
 // (X_low, gradient terms, the bin T/2), which the first CTA of the group writes.
-template <int NR, int KJ, bool BWD, bool EXT = false>
-__device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const FastParams& prm, int b, int d0, int ff1, int lane, bool side = true) {
+template <int NR, int KJ, bool BWD, bool EXT = false, int P = 1>
+__device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const FastParams& prm, int b, int d0, int ff1, int lane, bool side = true,
+                                                   cf* ybuf = nullptr, int tile = 0, int tid = 0) {
     constexpr int NJ = 2 * KJ;
     const int D = prm.D;
     const bool pvalid = d0 < D;
-    const bool grads = BWD && prm.gw_re != nullptr && side;
+    const bool rank1 = EXT && prm.h_re != nullptr;
+    const bool hgrads = EXT && BWD && rank1 && prm.hpart != nullptr && side;   // channel-contracted filter gradient through ybuf
+    const bool grads = BWD && prm.gw_re != nullptr && side && !hgrads;
+    float ch0 = 0.f, ch1 = 0.f, bg0 = 0.f, bg1 = 0.f;
+    if constexpr (EXT) {
+        if (rank1 && pvalid) {
+            ch0 = __ldg(prm.chan + d0); ch1 = __ldg(prm.chan + d0 + 1);
+            if (prm.bg != nullptr) { bg0 = __ldg(prm.bg + d0); bg1 = __ldg(prm.bg + d0 + 1); }
+        }
+        if (hgrads) __syncthreads();   // every warp has finished reading the exchange buffer of the last analysis pass
+    }
     const bool want_ds = EXT && BWD && prm.d_core != nullptr && side;   // needs X_low like the filter gradient
     float ec0 = 0.f, ec1 = 0.f, eq0 = 0.f, eq1 = 0.f;
     // EXT: per-(batch element, channel) factor on the filtered spectrum, and the raw analysis value of the bin -T/2
@@ -289,27 +311,65 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
     // Per chunk of JB bins: 1. issue every global load of the chunk up front (filter rows; BWD: saved X_low rows) so that
     // their latencies overlap -- the transform registers are dead here, so the values fit; 2. each thread filters its
     // non-negative bins and serves the mirror bins of its partner lane.
-    constexpr int JB = KJ <= 12 ? KJ : 8;
+    constexpr int JB = KJ <= 12 ? KJ : 8;   // (chunks of 4 for the extended backward at KJ = 32 remove its ~400 bytes of spills but cost more load rounds: 473 vs 408 us)
     static_assert(KJ % JB == 0, "chunking of the mid phase");
     cf self_mirror = acc[0];   // ff1 == 0: the mirror of bin NR*j is the own bin at index NJ - j (DC mirrors itself)
 #pragma unroll
     for (int j0 = 0; j0 < KJ; j0 += JB) {
         float wv[JB][4];
         float2 xv[JB][2];
+        float2 hv[EXT ? JB : 1];   // rank-one mode: H[f] itself (the gradient terms are taken against H, not chan * H)
+        float2 qv[EXT ? JB : 1];   // rank-one spectral bias Q[f] (FWD) / the d_q terms (BWD)
+        // all global loads of the chunk are issued before anything depends on them; the mode branches sit OUTSIDE the unrolled
+        // loops (a branch per bin serialises the loads: measured 2x on the whole kernel)
+        bool done = false;
+        if constexpr (EXT) {
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj) hv[jj] = qv[jj] = make_float2(0.f, 0.f);
+            if (rank1) {
+#pragma unroll
+                for (int jj = 0; jj < JB; ++jj) {
+                    const int af = ff1 + NR * (j0 + jj);
+                    if (pvalid && af < prm.k) hv[jj] = make_float2(__ldg(prm.h_re + af), __ldg(prm.h_im + af));
+                }
+                done = true;
+            }
+            if (prm.q_re != nullptr) {
+#pragma unroll
+                for (int jj = 0; jj < JB; ++jj) {
+                    const int af = ff1 + NR * (j0 + jj);
+                    if (pvalid && af < prm.k) qv[jj] = make_float2(__ldg(prm.q_re + af), __ldg(prm.q_im + af));
+                }
+            }
+        }
+        if (!done) {
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj) {
+                const int af = ff1 + NR * (j0 + jj);
+                wv[jj][0] = wv[jj][1] = wv[jj][2] = wv[jj][3] = 0.f;
+                if (pvalid && af < prm.k) {
+                    wv[jj][0] = __ldg(prm.w_re + wrow0 + af);
+                    wv[jj][1] = __ldg(prm.w_im + wrow0 + af);
+                    wv[jj][2] = __ldg(prm.w_re + wrow1 + af);
+                    wv[jj][3] = __ldg(prm.w_im + wrow1 + af);
+                }
+            }
+        }
 #pragma unroll
         for (int jj = 0; jj < JB; ++jj) {
             const int af = ff1 + NR * (j0 + jj);
-            const bool live = pvalid && af < prm.k;
-            wv[jj][0] = wv[jj][1] = wv[jj][2] = wv[jj][3] = 0.f;
             xv[jj][0] = xv[jj][1] = make_float2(0.f, 0.f);
-            if (live) {
-                wv[jj][0] = __ldg(prm.w_re + wrow0 + af);
-                wv[jj][1] = __ldg(prm.w_im + wrow0 + af);
-                wv[jj][2] = __ldg(prm.w_re + wrow1 + af);
-                wv[jj][3] = __ldg(prm.w_im + wrow1 + af);
-                if (grads || want_ds) {
-                    xv[jj][0] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
-                    xv[jj][1] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
+            if (pvalid && af < prm.k && (grads || want_ds || hgrads)) {
+                xv[jj][0] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
+                xv[jj][1] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
+            }
+        }
+        if constexpr (EXT) {
+            if (rank1) {
+#pragma unroll
+                for (int jj = 0; jj < JB; ++jj) {
+                    wv[jj][0] = ch0 * hv[jj].x; wv[jj][1] = ch0 * hv[jj].y;
+                    wv[jj][2] = ch1 * hv[jj].x; wv[jj][3] = ch1 * hv[jj].y;
                 }
             }
         }
@@ -333,14 +393,12 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
             const float gdc0 = s0.re, gdc1 = s1.re;   // BWD: sum_t g of the two channels when af == 0 (before any scaling)
             if constexpr (EXT && BWD) {
                 if (want_ds && live) {   // dL/dscale terms of this bin, from the unscaled G
-                    const cf A0 = cmul(cf{xv[jj][0].x, xv[jj][0].y}, w0), A1 = cmul(cf{xv[jj][1].x, xv[jj][1].y}, w1);
+                    const cf wd0 = rank1 ? cf{hv[jj].x, hv[jj].y} : w0, wd1 = rank1 ? cf{hv[jj].x, hv[jj].y} : w1;
+                    const cf A0 = cmul(cf{xv[jj][0].x, xv[jj][0].y}, wd0), A1 = cmul(cf{xv[jj][1].x, xv[jj][1].y}, wd1);
                     ec0 = fmaf(s0.re, A0.re, fmaf(s0.im, A0.im, ec0));
                     ec1 = fmaf(s1.re, A1.re, fmaf(s1.im, A1.im, ec1));
-                    if (prm.q_re != nullptr) {
-                        const float qr = __ldg(prm.q_re + af), qi = __ldg(prm.q_im + af);
-                        eq0 = fmaf(s0.re, qr, fmaf(s0.im, qi, eq0));
-                        eq1 = fmaf(s1.re, qr, fmaf(s1.im, qi, eq1));
-                    }
+                    eq0 = fmaf(s0.re, qv[jj].x, fmaf(s0.im, qv[jj].y, eq0));   // (qv = 0 without Q)
+                    eq1 = fmaf(s1.re, qv[jj].x, fmaf(s1.im, qv[jj].y, eq1));
                 }
                 // y = scale * ifft(W X): the gradient entering the filter is scale * G
                 s0 = cf{s0.re * sc0, s0.im * sc0};
@@ -358,11 +416,20 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
                     if (prm.sb_re != nullptr && live) {
                         a0 = cf{a0.re + __ldg(prm.sb_re + wrow0 + af), a0.im + __ldg(prm.sb_im + wrow0 + af)};
                         a1 = cf{a1.re + __ldg(prm.sb_re + wrow1 + af), a1.im + __ldg(prm.sb_im + wrow1 + af)};
+                    } else if (rank1) {   // bg = 0 / qv = 0 where they are not given
+                        a0 = cf{fmaf(bg0, qv[jj].x, a0.re), fmaf(bg0, qv[jj].y, a0.im)};
+                        a1 = cf{fmaf(bg1, qv[jj].x, a1.re), fmaf(bg1, qv[jj].y, a1.im)};
                     }
                     a0 = cf{a0.re * sc0, a0.im * sc0};
                     a1 = cf{a1.re * sc1, a1.im * sc1};
                 }
             } else {
+                if constexpr (EXT) {
+                    if (hgrads && af < prm.k) {   // sum over this thread's two channels; the P pairs meet in the exchange buffer
+                        const cf g0 = cmulc(s0, cf{xv[jj][0].x, xv[jj][0].y}), g1 = cmulc(s1, cf{xv[jj][1].x, xv[jj][1].y});   // zero when !pvalid
+                        ybuf[(size_t)(tid / NR) * (KJ * NR) + af] = cf{(ch0 * g0.re + ch1 * g1.re) * prm.invT, (ch0 * g0.im + ch1 * g1.im) * prm.invT};
+                    }
+                }
                 if (live && grads) {
                     const cf g0 = cmulc(s0, cf{xv[jj][0].x, xv[jj][0].y});   // G conj(X)
                     const cf g1 = cmulc(s1, cf{xv[jj][1].x, xv[jj][1].y});
@@ -401,6 +468,18 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
         acc[KJ] = cf{0.f, 0.f};
     }
     if constexpr (EXT && BWD) {
+        if (hgrads) {   // (uniform over the CTA) sum the P partial spectra and write this work item's k bins
+            __syncthreads();
+            for (int idx = tid; idx < prm.k; idx += NR * P) {
+                cf sum = ybuf[idx];
+#pragma unroll
+                for (int p = 1; p < P; ++p) sum = cadd(sum, ybuf[(size_t)p * (KJ * NR) + idx]);
+                reinterpret_cast<float2*>(prm.hpart)[(size_t)tile * prm.k + idx] = make_float2(sum.re, sum.im);
+            }
+            // (the first synthesis pass writes the exchange buffer only after its barrier (A'))
+        }
+    }
+    if constexpr (EXT && BWD) {
         if (prm.d_core != nullptr) {   // (uniform branch: every lane takes part in the shuffles)
 #pragma unroll
             for (int o = NR / 2; o > 0; o >>= 1) {   // sum over the NR lanes (f1) that share this channel pair
@@ -412,8 +491,10 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
             if (want_ds && ff1 == 0 && pvalid) {
                 const size_t o = (size_t)b * D + d0;
                 if (prm.wnyq != nullptr && prm.xnyq != nullptr) {   // bin T/2: G and X real there
-                    ec0 = fmaf(znyq.re, prm.xnyq[o] * __ldg(prm.wnyq + d0), ec0);
-                    ec1 = fmaf(znyq.im, prm.xnyq[o + 1] * __ldg(prm.wnyq + d0 + 1), ec1);
+                    const float wd0 = rank1 ? (prm.h_nyq != nullptr ? __ldg(prm.h_nyq) : 0.f) : __ldg(prm.wnyq + d0);
+                    const float wd1 = rank1 ? wd0 : __ldg(prm.wnyq + d0 + 1);
+                    ec0 = fmaf(znyq.re, prm.xnyq[o] * wd0, ec0);
+                    ec1 = fmaf(znyq.im, prm.xnyq[o + 1] * wd1, ec1);
                     const float qn = prm.q_nyq != nullptr ? __ldg(prm.q_nyq) : 0.f;
                     eq0 = fmaf(znyq.re, qn, eq0);
                     eq1 = fmaf(znyq.im, qn, eq1);
@@ -727,7 +808,7 @@ __global__ void __launch_bounds__(NR* P, MINB)
                 }
             }
         }
-        spectral_mid_phase<NR, KJ, BWD, EXT>(acc, prm, b, dt * 2 * P + 2 * fp2, ff1, tid & 31, member == 0);
+        spectral_mid_phase<NR, KJ, BWD, EXT, P>(acc, prm, b, dt * 2 * P + 2 * fp2, ff1, tid & 31, member == 0, ybuf, tile, tid);
 
         // ===================== synthesis: transpose of analysis; rows leave through a TMA store from X =====================
         // staging tile: the tile of this work item's last load, drained by every warp (barrier (A')); with a residual the

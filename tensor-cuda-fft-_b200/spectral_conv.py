@@ -50,83 +50,78 @@ def _aligned(t: torch.Tensor) -> torch.Tensor:
 class _CausalSpectralConvFn(torch.autograd.Function):
     """y[:, :T] = residual + s[b,c] * irfft( (gamma x^ + beta rect)~ * gain[c] * H[f] )[:T]   (x^ = LayerNorm rows without affine)
 
-    Inputs (all effective arrays are built by the caller with ordinary autograd ops from the block's parameters):
-      x (B,T,C); w_re, w_im (C, n/2): gamma*gain*H with the factor 2 on bins >= 1; w_nyq (C,): gamma*gain*Re H[n/2];
-      beta_gain (C,) = beta*gain; q_re, q_im (n/2,), q_nyq (): rfft(rect_T)*H in the same convention (no gradient: the beta path's
-      gradient flows through ``u``); u (T,) = the time response of the beta path, irfft(rfft(rect_T) H)[:T];
+    The multiplier is rank one in (channel, frequency): the kernel forms ``chan[c] * H[f]`` itself (``sml_ext`` rank-one mode), so no
+    (C, F) array exists on either side.  Inputs (built by the caller with ordinary autograd ops from the block's parameters):
+      x (B,T,C); h_re, h_im (n/2,): H with the factor 2 on bins >= 1 (the kernel keeps Re(ifft(.)) semantics); h_nyq (): Re H[n/2];
+      chan (C,) = gamma*gain; beta_gain (C,) = beta*gain; q_re, q_im (n/2,), q_nyq (): rfft(rect_T)*H in the same convention (no
+      gradient: the beta path's gradient with respect to H flows through ``u``); u (T,) = irfft(rfft(rect_T) H)[:T];
       gamma, beta (C,), gate_w (C,C), gate_b (C,): the context gate s = sigmoid(gate(mean_t LayerNorm(x))) (train_fixed_full.py:531-533);
-      eps; add_residual (False: return the convolution alone, for a dropout between it and the skip connection).
+      eps; n_fft; add_residual (False: return the convolution alone, for a dropout between it and the skip connection).
     """
 
     @staticmethod
-    def forward(ctx, x, w_re, w_im, w_nyq, beta_gain, q_re, q_im, q_nyq, u, gamma, beta, gate_w, gate_b, eps, n_fft, add_residual):
+    def forward(ctx, x, h_re, h_im, h_nyq, chan, beta_gain, q_re, q_im, q_nyq, u, gamma, beta, gate_w, gate_b, eps, n_fft, add_residual):
         B, T, C = x.shape
         io = _IO_DTYPES[x.dtype]
         Fn = n_fft // 2
         lib = _native.lib()
         dev = x.device
         xc = _aligned(x)
-        wr, wi, wn = _f32c(w_re), _f32c(w_im), _f32c(w_nyq)
+        hr, hi, hn = _f32c(h_re), _f32c(h_im), _f32c(h_nyq).reshape(1)
+        qr, qi, qn = _f32c(q_re), _f32c(q_im), _f32c(q_nyq).reshape(1)
+        ch, bg = _f32c(chan), _f32c(beta_gain)
         stats = torch.empty(B, n_fft, 2, dtype=torch.float32, device=dev)
         with _on_device(dev):
-            st = _stream_handle(dev)
-            _native.check(lib.sml_ln_stats(_ptr(xc), _ptr(stats), B, n_fft, T, 0, C, float(eps), io, st))
+            _native.check(lib.sml_ln_stats(_ptr(xc), _ptr(stats), B, n_fft, T, 0, C, float(eps), io, _stream_handle(dev)))
         mean, rstd = stats[:, :T, 0], stats[:, :T, 1]
         # context gate: pooled = mean_t LayerNorm(x) = gamma * mean_t x^ + beta ; mean_t x^ from the row statistics and ONE
         # batched matrix-vector product over x (the normalised tensor is never materialised)
         mhat = (torch.bmm(rstd.to(xc.dtype).unsqueeze(1), xc).squeeze(1).float() - (mean * rstd).sum(1, keepdim=True)) / T
         pooled = gamma.float() * mhat + beta.float()
         s = torch.sigmoid(F.linear(pooled, gate_w.float(), gate_b.float())).contiguous()
-        bg = beta_gain.detach().float()
-        sb_re = (bg[:, None] * q_re.detach().float()[None, :]).contiguous()
-        sb_im = (bg[:, None] * q_im.detach().float()[None, :]).contiguous()
-        sb_nyq = (bg * q_nyq.detach().float()).contiguous()
+        w_nyq = (ch * hn).contiguous()          # (C,) vectors for the bin n/2
+        sb_nyq = (bg * qn).contiguous()
         y = torch.empty_like(xc)
         # the saved spectrum serves the filter gradient AND the gate gradient (d_core, which also feeds dL/dx through the pooled
         # context): needed whenever anything is differentiated
-        need_filter_grad = any(ctx.needs_input_grad)
-        xlow = torch.empty(max(_shape_info(B, n_fft, C, Fn, io)[1] // 8, 1), dtype=torch.complex64, device=dev) if need_filter_grad else None
+        need_spectrum = any(ctx.needs_input_grad)
+        xlow = torch.empty(max(_shape_info(B, n_fft, C, Fn, io)[1] // 8, 1), dtype=torch.complex64, device=dev) if need_spectrum else None
         xnyq = torch.empty(B, C, dtype=torch.float32, device=dev)
-        ext = _native.make_ext(row_stats=stats, residual=xc if add_residual else None, chan_scale=s, w_nyq=wn, sb_re=sb_re,
-                               sb_im=sb_im, sb_nyq=sb_nyq, x_nyq=xnyq, T_in=T, T_out=T)
+        ext = _native.make_ext(row_stats=stats, residual=xc if add_residual else None, chan_scale=s, w_nyq=w_nyq, sb_nyq=sb_nyq, x_nyq=xnyq,
+                               h_re=hr, h_im=hi, h_nyq=hn, chan=ch, bg=bg, q_re=qr, q_im=qi, q_nyq=qn, T_in=T, T_out=T)
         with _on_device(dev):
-            _native.check(lib.sml_forward_ext(_ptr(xc), _ptr(wr), _ptr(wi), None, _ptr(y), _ptr(xlow), B, n_fft, C, Fn, io,
-                                              ctypes.byref(ext), _stream_handle(dev)))
-        qr, qi, qn = _f32c(q_re), _f32c(q_im), _f32c(q_nyq).reshape(1)
-        ctx.save_for_backward(xc, stats, wr, wi, wn, xlow, xnyq, s, pooled, mhat, beta_gain, gamma, gate_w, qr, qi, qn)
+            _native.check(lib.sml_forward_ext(_ptr(xc), None, None, None, _ptr(y), _ptr(xlow), B, n_fft, C, Fn, io, ctypes.byref(ext),
+                                              _stream_handle(dev)))
+        ctx.save_for_backward(xc, stats, hr, hi, hn, ch, bg, qr, qi, qn, w_nyq, xlow, xnyq, s, pooled, mhat, gamma, gate_w)
         ctx.cfg = (B, T, C, Fn, io, n_fft, add_residual)
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        xc, stats, wr, wi, wn, xlow, xnyq, s, pooled, mhat, beta_gain, gamma, gate_w, qr, qi, qn = ctx.saved_tensors
+        xc, stats, hr, hi, hn, ch, bg, qr, qi, qn, w_nyq, xlow, xnyq, s, pooled, mhat, gamma, gate_w = ctx.saved_tensors
         B, T, C, Fn, io, n_fft, add_residual = ctx.cfg
         lib = _native.lib()
         dev = g.device
         gc = _aligned(g.to(xc.dtype))
-        want = xlow is not None
-        gwr = gwi = gb = ws = None
-        ws_bytes = 0
-        if want:
-            flat = torch.empty(2 * C * Fn + C, dtype=torch.float32, device=dev)
-            gwr, gwi, gb = flat[: C * Fn].view(C, Fn), flat[C * Fn: 2 * C * Fn].view(C, Fn), flat[2 * C * Fn:]
-            ws_bytes = _shape_info(B, n_fft, C, Fn, io)[2]
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rows = int(lib.sml_ext_hpart_rows(B, n_fft, C, Fn, io))
+        hpart = torch.empty(rows, Fn, dtype=torch.complex64, device=dev)      # channel-contracted filter gradient, one row per work item
         gnyq = torch.empty(B, C, dtype=torch.float32, device=dev)
-        gh = torch.empty_like(gc)
         d_core = torch.empty(B, C, dtype=torch.float32, device=dev)
         d_q = torch.empty(B, C, dtype=torch.float32, device=dev)
-        ext = _native.make_ext(chan_scale=s, w_nyq=wn, x_nyq=xnyq, g_nyq=gnyq, T_in=T, T_out=T, d_core=d_core, d_q=d_q, q_re=qr, q_im=qi,
-                               q_nyq=qn)
+        gh = torch.empty_like(gc)
+        ext = _native.make_ext(chan_scale=s, w_nyq=w_nyq, x_nyq=xnyq, g_nyq=gnyq, T_in=T, T_out=T, d_core=d_core, d_q=d_q, q_re=qr, q_im=qi,
+                               q_nyq=qn, h_re=hr, h_im=hi, h_nyq=hn, chan=ch, bg=bg, hpart=hpart)
         with _on_device(dev):
-            _native.check(lib.sml_backward_ext(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gh), _ptr(gwr), _ptr(gwi), _ptr(gb),
-                                               _ptr(ws), ws_bytes, B, n_fft, C, Fn, io, ctypes.byref(ext), _stream_handle(dev)))
+            _native.check(lib.sml_backward_ext(_ptr(gc), _ptr(xlow), None, None, _ptr(gh), None, None, None, None, 0, B, n_fft, C, Fn, io,
+                                               ctypes.byref(ext), _stream_handle(dev)))
+        dH = hpart.sum(0)                                       # dL/dH in the kernel's (gw_re + i gw_im) convention
+        d_h_nyq = (gnyq * ch).sum()
         # gate: dL/ds[b,c] = sum_t g * (y - residual) / s, evaluated by the backward kernel in the spectral domain (it holds G, X_low and
-        # the filter anyway): (1/T) sum_f Re(conj(G) (X W + beta_gain[c] Q)) = d_core + beta_gain[c] * d_q -- no pass over y, and y
-        # is not kept for the backward
-        bgf = beta_gain.float()
-        ds = d_core + bgf * d_q
+        # H anyway): d_core = (1/T) sum_f Re(conj(G) X H), d_q = (1/T) sum_f Re(conj(G) Q) -- no pass over y, y is not kept
+        ds = ch * d_core + bg * d_q
+        d_chan = (s * d_core).sum(0)
+        d_beta_gain = (s * d_q).sum(0)
         dz = ds * s * (1.0 - s)
         d_gate_w = dz.t() @ pooled
         d_gate_b = dz.sum(0)
@@ -134,12 +129,9 @@ class _CausalSpectralConvFn(torch.autograd.Function):
         d_gamma = (dpooled * mhat).sum(0)
         d_beta = dpooled.sum(0)
         dmhat = dpooled * gamma.float()                       # d/d(mean_t x^): spreads over the T rows as dmhat / T
-        # beta path: y_beta[b,t,c] = s[b,c] * beta_gain[c] * u[t]
-        #   d_beta_gain[c] = sum_b s[b,c] * d_q[b,c] ;  d_u[t] = sum_b (g[b] (s[b] * beta_gain))[t]  (one batched matrix-vector product over g)
-        d_beta_gain = (s * d_q).sum(0)
-        d_u = torch.bmm(gc, (s * bgf).to(gc.dtype).unsqueeze(2)).squeeze(2).float().sum(0)
-        # LayerNorm backward (+ the skip connection's gradient, + the pooled-mean term) in one pass
-        # (the pooled-mean term enters dL/dx^ as the per-(b, c) constant dmhat / T: chan_add of the same kernel)
+        # beta path, y_beta[b,t,c] = s[b,c] * beta_gain[c] * u[t]:  d_u[t] = sum_b (g[b] (s[b] * beta_gain))[t]  (one batched matrix-vector product)
+        d_u = torch.bmm(gc, (s * bg).to(gc.dtype).unsqueeze(2)).squeeze(2).float().sum(0)
+        # LayerNorm backward (+ the skip connection's gradient, + the pooled-mean term dmhat / T as chan_add) in one pass
         chan_add = (dmhat / T).contiguous()
         gx = torch.empty_like(gc)
         with _on_device(dev):
@@ -147,12 +139,11 @@ class _CausalSpectralConvFn(torch.autograd.Function):
                                               _ptr(gx), B, n_fft, T, 0, C, io, _stream_handle(dev)))
         need = ctx.needs_input_grad
         return (gx if need[0] else None,
-                gwr if (want and need[1]) else None, gwi if (want and need[2]) else None,
-                gnyq.sum(0) if need[3] else None,
-                d_beta_gain if need[4] else None, None, None, None,
-                d_u if need[8] else None,
-                d_gamma if need[9] else None, d_beta if need[10] else None,
-                d_gate_w if need[11] else None, d_gate_b if need[12] else None,
+                dH.real if need[1] else None, dH.imag if need[2] else None, d_h_nyq if need[3] else None,
+                d_chan if need[4] else None, d_beta_gain if need[5] else None, None, None, None,
+                d_u if need[9] else None,
+                d_gamma if need[10] else None, d_beta if need[11] else None,
+                d_gate_w if need[12] else None, d_gate_b if need[13] else None,
                 None, None, None)
 
 
@@ -237,15 +228,18 @@ class FixedSpectralBlock(nn.Module):
         H = _multiplier(self.kernel, self.gate_freq_logits, n, self.kernel_len, cutoff, self.transition_bins)
         gamma, beta = self.ln.weight.float(), self.ln.bias.float()
         gain = self.gain.float()
-        w_re, w_im, w_nyq = _kernel_filter(H, gamma * gain)
+        Fn = n // 2
+        two = torch.cat([torch.ones(1, device=x.device), torch.full((Fn - 1,), 2.0, device=x.device)])   # Re(ifft(.)) convention of the kernel
+        H2 = H[:Fn] * two
         # beta path: a LayerNorm bias on the T real rows of a zero-padded window is beta * rect_T
         rect = torch.cat([torch.ones(T, device=x.device), torch.zeros(n - T, device=x.device)])
         Q = torch.fft.rfft(rect) * H
         u = torch.fft.irfft(Q, n=n)[:T]
-        q_re, q_im, q_nyq = _kernel_filter(Q.detach(), torch.ones(1, device=x.device))
+        Qd = Q.detach()
+        Q2 = Qd[:Fn] * two
         fuse_res = not (self.training and self.drop.p > 0.0)
-        y = _CausalSpectralConvFn.apply(x, w_re, w_im, w_nyq, beta * gain, q_re[0], q_im[0], q_nyq[0], u, gamma, beta,
-                                        self.gate_ctx.weight, self.gate_ctx.bias, self.ln.eps, n, fuse_res)
+        y = _CausalSpectralConvFn.apply(x, H2.real, H2.imag, H[Fn].real, gamma * gain, beta * gain, Q2.real, Q2.imag, Qd[Fn].real, u,
+                                        gamma, beta, self.gate_ctx.weight, self.gate_ctx.bias, self.ln.eps, n, fuse_res)
         if not fuse_res:
             y = x + self.drop(y)
         return y
