@@ -143,11 +143,12 @@ typedef struct sml_ext {
     const float* sb_nyq;      /*   Forward only; all three or none (sb_nyq only with w_nyq).                                   */
     float* x_nyq;             /* (B, D): spectrum at the bin T/2; written by the forward, read by the backward */
     float* g_nyq;             /* (B, D): backward only: per-batch-element gradient terms of w_nyq (sum over B outside) */
-    float* d_core;            /* (B, D): backward only: (1/T) sum_f Re(conj(G) X W) incl. the bin T/2 -- with d_q the gradient of      */
-    float* d_q;               /*   chan_scale without a pass over y: dL/dchan_scale[b,c] = d_core + bg[c] * d_q for sb = bg[c] * Q[f]; */
-    const float* q_re;        /*   d_q[b,c] = (1/T) sum_f Re(conj(G) Q), Q = (q_re, q_im) of shape (F,), q_nyq its bin T/2.            */
-    const float* q_im;        /*   Needs xlow.  All nullable.                                                                        */
-    const float* q_nyq;       /*   (1,) device scalar                                                                                */
+    float* d_core;            /* (B, D): backward only: (1/T) sum_f Re(conj(G) X W) incl. the bin T/2 (rank-one mode: against H instead of W)   */
+    float* d_q;               /* (B, D): backward only: (1/T) sum_f Re(conj(G) Q).  Together the gradient of chan_scale without a pass over  */
+                              /*   y: dL/dchan_scale[b,c] = d_core (+ bg[c] * d_q when the spectral bias is bg[c] * Q[f]).  Need xlow.       */
+    const float* q_re;        /* (F,) Q: the d_q terms of the backward; in rank-one mode also the forward's spectral bias bg[d] * Q[f]       */
+    const float* q_im;        /* (F,) */
+    const float* q_nyq;       /* (1,) device scalar: Q at the bin T/2 */
     /* Rank-one filter mode (h_re != NULL; w_re / w_im of the call may then be NULL): w[d,f] = chan[d] * (h_re, h_im)[f] and, in the
      * forward, sb[d,f] = bg[d] * (q_re, q_im)[f] are formed inside the kernel -- the multiplier of FixedSpectralBlock is
      * gain[c] * H[f], there is no (D, F) array to read.  w_nyq / sb_nyq stay (D,) vectors.  Backward: the filter gradient is
