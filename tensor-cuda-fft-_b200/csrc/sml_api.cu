@@ -44,7 +44,7 @@ const Knobs& knobs() {
         if (const char* e = getenv("SML_FAST_CTAS")) v.fast_ctas = atoi(e);
         if (const char* e = getenv("SML_FAST_XB")) v.fast_xb = atoi(e);
         if (const char* e = getenv("SML_TC")) v.tc = atoi(e) != 0 ? 1 : 0;
-        if (const char* e = getenv("SML_PDL")) v.pdl = atoi(e) != 0 ? 1 : 0;
+        if (const char* e = getenv("SML_PDL")) v.pdl = atoi(e);   // 1: every kernel of the chain; 2: only the small batch-reduction kernel
         if (const char* e = getenv("SML_EXT_CTAS")) v.ext_ctas = atoi(e);
         if (const char* e = getenv("SML_SPLIT")) v.split = atoi(e);
         return v;
@@ -423,11 +423,11 @@ int launch_filtergrad_reduce(const sml::cf* gpart, const float* gbpart, float* g
                       (flat_mc == nullptr || (((uintptr_t)flat_mc % 16 == 0) && ((uintptr_t)flat_next % 16 == 0)));
     if (vec4) {
         const long long n = (long long)D * (F / 4);
-        SML_CUDA(sml_host::launch_pdl(sml::filtergrad_reduce4_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
+        SML_CUDA(sml_host::launch_pdl_if(knobs().pdl >= 1, sml::filtergrad_reduce4_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
                                       reinterpret_cast<const float2*>(gpart), gbpart, gw_re, gw_im, gb, B, D, F, k, flat_mc, flat_next));
     } else {
         const long long n = (long long)D * ((F + 1) / 2);
-        SML_CUDA(sml_host::launch_pdl(sml::filtergrad_reduce_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
+        SML_CUDA(sml_host::launch_pdl_if(knobs().pdl >= 1, sml::filtergrad_reduce_kernel, dim3((unsigned)((n + 63) / 64)), dim3(64, 4), 0, stream,
                                       reinterpret_cast<const float2*>(gpart), gbpart, gw_re, gw_im, gb, B, D, F, k, flat_mc, flat_next));
     }
     count_launch();

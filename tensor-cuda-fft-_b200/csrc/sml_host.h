@@ -41,7 +41,7 @@ int get_encode_fn(EncodeTiledFn* out);
 // table staging) while its predecessor in the stream drains; every kernel of this library executes griddepcontrol.wait
 // before it touches global data another kernel may have written, and triggers its own dependents right after that.
 template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+cudaError_t launch_pdl_if(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -51,8 +51,12 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = knobs().pdl ? 1u : 0u;
+    cfg.numAttrs = pdl ? 1u : 0u;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    return launch_pdl_if(knobs().pdl == 1, kern, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 
 // ---- tensor-core path (sml_inst_tc.cu) ----
