@@ -146,7 +146,7 @@ typedef struct sml_ext {
     float* d_core;            /* (B, D): backward only: (1/T) sum_f Re(conj(G) X W) incl. the bin T/2 (rank-one mode: against H instead of W)   */
     float* d_q;               /* (B, D): backward only: (1/T) sum_f Re(conj(G) Q).  Together the gradient of chan_scale without a pass over  */
                               /*   y: dL/dchan_scale[b,c] = d_core (+ bg[c] * d_q when the spectral bias is bg[c] * Q[f]).  Need xlow.       */
-    const float* q_re;        /* (F,) Q: the d_q terms of the backward; in rank-one mode also the forward's spectral bias bg[d] * Q[f]       */
+    const float* q_re;        /* (F,) Q, rank-one mode only: the d_q terms of the backward and the forward's spectral bias bg[d] * Q[f]      */
     const float* q_im;        /* (F,) */
     const float* q_nyq;       /* (1,) device scalar: Q at the bin T/2 */
     /* Rank-one filter mode (h_re != NULL; w_re / w_im of the call may then be NULL): w[d,f] = chan[d] * (h_re, h_im)[f] and, in the

@@ -316,37 +316,40 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
     cf self_mirror = acc[0];   // ff1 == 0: the mirror of bin NR*j is the own bin at index NJ - j (DC mirrors itself)
 #pragma unroll
     for (int j0 = 0; j0 < KJ; j0 += JB) {
-        float wv[JB][4];
+        float wv[JB][4];   // (D, F) filter of the two channels -- or, in rank-one mode, H[f] in [0..1] and Q[f] in [2..3]
         float2 xv[JB][2];
-        float2 hv[EXT ? JB : 1];   // rank-one mode: H[f] itself (the gradient terms are taken against H, not chan * H)
-        float2 qv[EXT ? JB : 1];   // rank-one spectral bias Q[f] (FWD) / the d_q terms (BWD)
-        // all global loads of the chunk are issued before anything depends on them; the mode branches sit OUTSIDE the unrolled
+        // all global loads of the chunk are issued before anything depends on them; the mode branch sits OUTSIDE the unrolled
         // loops (a branch per bin serialises the loads: measured 2x on the whole kernel)
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) wv[jj][0] = wv[jj][1] = wv[jj][2] = wv[jj][3] = 0.f;
         bool done = false;
         if constexpr (EXT) {
-#pragma unroll
-            for (int jj = 0; jj < JB; ++jj) hv[jj] = qv[jj] = make_float2(0.f, 0.f);
             if (rank1) {
 #pragma unroll
                 for (int jj = 0; jj < JB; ++jj) {
                     const int af = ff1 + NR * (j0 + jj);
-                    if (pvalid && af < prm.k) hv[jj] = make_float2(__ldg(prm.h_re + af), __ldg(prm.h_im + af));
+                    if (pvalid && af < prm.k) {
+                        wv[jj][0] = __ldg(prm.h_re + af);
+                        wv[jj][1] = __ldg(prm.h_im + af);
+                    }
+                }
+                if (prm.q_re != nullptr) {
+#pragma unroll
+                    for (int jj = 0; jj < JB; ++jj) {
+                        const int af = ff1 + NR * (j0 + jj);
+                        if (pvalid && af < prm.k) {
+                            wv[jj][2] = __ldg(prm.q_re + af);
+                            wv[jj][3] = __ldg(prm.q_im + af);
+                        }
+                    }
                 }
                 done = true;
-            }
-            if (prm.q_re != nullptr) {
-#pragma unroll
-                for (int jj = 0; jj < JB; ++jj) {
-                    const int af = ff1 + NR * (j0 + jj);
-                    if (pvalid && af < prm.k) qv[jj] = make_float2(__ldg(prm.q_re + af), __ldg(prm.q_im + af));
-                }
             }
         }
         if (!done) {
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) {
                 const int af = ff1 + NR * (j0 + jj);
-                wv[jj][0] = wv[jj][1] = wv[jj][2] = wv[jj][3] = 0.f;
                 if (pvalid && af < prm.k) {
                     wv[jj][0] = __ldg(prm.w_re + wrow0 + af);
                     wv[jj][1] = __ldg(prm.w_im + wrow0 + af);
@@ -362,15 +365,6 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
             if (pvalid && af < prm.k && (grads || want_ds || hgrads)) {
                 xv[jj][0] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow0 + af);
                 xv[jj][1] = __ldg(reinterpret_cast<const float2*>(prm.xlow) + xrow1 + af);
-            }
-        }
-        if constexpr (EXT) {
-            if (rank1) {
-#pragma unroll
-                for (int jj = 0; jj < JB; ++jj) {
-                    wv[jj][0] = ch0 * hv[jj].x; wv[jj][1] = ch0 * hv[jj].y;
-                    wv[jj][2] = ch1 * hv[jj].x; wv[jj][3] = ch1 * hv[jj].y;
-                }
             }
         }
 #pragma unroll
@@ -389,16 +383,19 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
             // Hermitian split: spectra of the two real channels at +af
             cf s0 = cf{0.5f * (zp.re + zm.re), 0.5f * (zp.im - zm.im)};
             cf s1 = cf{0.5f * (zp.im + zm.im), 0.5f * (zm.re - zp.re)};
-            const cf w0 = cf{wv[jj][0], wv[jj][1]}, w1 = cf{wv[jj][2], wv[jj][3]};
+            const cf hq = cf{wv[jj][0], wv[jj][1]};                                  // rank-one mode: H[f]
+            const cf qq = rank1 ? cf{wv[jj][2], wv[jj][3]} : cf{0.f, 0.f};           // rank-one mode: Q[f]
+            const cf w0 = rank1 ? cf{ch0 * hq.re, ch0 * hq.im} : hq;
+            const cf w1 = rank1 ? cf{ch1 * hq.re, ch1 * hq.im} : cf{wv[jj][2], wv[jj][3]};
             const float gdc0 = s0.re, gdc1 = s1.re;   // BWD: sum_t g of the two channels when af == 0 (before any scaling)
             if constexpr (EXT && BWD) {
                 if (want_ds && live) {   // dL/dscale terms of this bin, from the unscaled G
-                    const cf wd0 = rank1 ? cf{hv[jj].x, hv[jj].y} : w0, wd1 = rank1 ? cf{hv[jj].x, hv[jj].y} : w1;
+                    const cf wd0 = rank1 ? hq : w0, wd1 = rank1 ? hq : w1;
                     const cf A0 = cmul(cf{xv[jj][0].x, xv[jj][0].y}, wd0), A1 = cmul(cf{xv[jj][1].x, xv[jj][1].y}, wd1);
                     ec0 = fmaf(s0.re, A0.re, fmaf(s0.im, A0.im, ec0));
                     ec1 = fmaf(s1.re, A1.re, fmaf(s1.im, A1.im, ec1));
-                    eq0 = fmaf(s0.re, qv[jj].x, fmaf(s0.im, qv[jj].y, eq0));   // (qv = 0 without Q)
-                    eq1 = fmaf(s1.re, qv[jj].x, fmaf(s1.im, qv[jj].y, eq1));
+                    eq0 = fmaf(s0.re, qq.re, fmaf(s0.im, qq.im, eq0));   // (Q = 0 outside the rank-one mode)
+                    eq1 = fmaf(s1.re, qq.re, fmaf(s1.im, qq.im, eq1));
                 }
                 // y = scale * ifft(W X): the gradient entering the filter is scale * G
                 s0 = cf{s0.re * sc0, s0.im * sc0};
@@ -417,8 +414,8 @@ __device__ __forceinline__ void spectral_mid_phase(cf (&acc)[2 * KJ], const Fast
                         a0 = cf{a0.re + __ldg(prm.sb_re + wrow0 + af), a0.im + __ldg(prm.sb_im + wrow0 + af)};
                         a1 = cf{a1.re + __ldg(prm.sb_re + wrow1 + af), a1.im + __ldg(prm.sb_im + wrow1 + af)};
                     } else if (rank1) {   // bg = 0 / qv = 0 where they are not given
-                        a0 = cf{fmaf(bg0, qv[jj].x, a0.re), fmaf(bg0, qv[jj].y, a0.im)};
-                        a1 = cf{fmaf(bg1, qv[jj].x, a1.re), fmaf(bg1, qv[jj].y, a1.im)};
+                        a0 = cf{fmaf(bg0, qq.re, a0.re), fmaf(bg0, qq.im, a0.im)};
+                        a1 = cf{fmaf(bg1, qq.re, a1.re), fmaf(bg1, qq.im, a1.im)};
                     }
                     a0 = cf{a0.re * sc0, a0.im * sc0};
                     a1 = cf{a1.re * sc1, a1.im * sc1};
