@@ -379,7 +379,7 @@ class SpectralEMA(nn.Module):
     def scan(self, fft_chunks: torch.Tensor, init: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.mode not in ("aligned", "polar"):
             raise ValueError(f"Unknown SpectralEMA mode: {self.mode}")
-        if torch.is_grad_enabled() and (fft_chunks.requires_grad or self.rho_logit.requires_grad and self.training
+        if torch.is_grad_enabled() and (fft_chunks.requires_grad or self.rho_logit.requires_grad or self.theta_raw.requires_grad
                                         or (init is not None and init.requires_grad)):
             # training: gradients flow into rho / theta and the chunks; the kernel is the inference path (no backward)
             state = torch.zeros((fft_chunks.shape[0], self.n_freqs), device=fft_chunks.device, dtype=torch.complex64) if init is None else init
