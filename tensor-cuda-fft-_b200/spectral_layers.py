@@ -255,6 +255,79 @@ class _LNSpectralResidualFn(torch.autograd.Function):
                 None)
 
 
+class _SpectralResidualFn(torch.autograd.Function):
+    """``x + spectral_mix(x)`` (HybridSpectralAttention feeds ``x + global_context`` to its norm, spectral_layers.py:243-248): the
+    skip connection is added while the fused kernel stores its rows (sml_forward_ext, residual = x) instead of by a separate
+    three-stream add; the backward is the plain fused backward plus the skip connection's gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w_re, w_im, bias):
+        import ctypes
+        B, T, D = x.shape
+        Fn = w_re.shape[1]
+        io = _IO_DTYPES[x.dtype]
+        lib = _native.lib()
+        xc = x.contiguous()
+        if xc.data_ptr() % 16:
+            xc = xc.clone()
+        wr, wi, bs = _f32c(w_re), _f32c(w_im), _f32c(bias)
+        y = torch.empty_like(xc)
+        need_filter_grad = any(ctx.needs_input_grad[1:])
+        xlow = torch.empty(max(_shape_info(B, T, D, Fn, io)[1] // 8, 1), dtype=torch.complex64, device=x.device) if need_filter_grad else None
+        ext = _native.make_ext(residual=xc)
+        with _on_device(x.device):
+            _native.check(lib.sml_forward_ext(_ptr(xc), _ptr(wr), _ptr(wi), _ptr(bs), _ptr(y), _ptr(xlow), B, T, D, Fn, io,
+                                              ctypes.byref(ext), _stream_handle(x.device)))
+        ctx.save_for_backward(wr, wi, xlow)
+        ctx.shape = (B, T, D, Fn, io)
+        ctx.dtypes = (x.dtype, w_re.dtype, w_im.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        wr, wi, xlow = ctx.saved_tensors
+        B, T, D, Fn, io = ctx.shape
+        lib = _native.lib()
+        gc = g.contiguous().to(ctx.dtypes[0])
+        if gc.data_ptr() % 16:
+            gc = gc.clone()
+        gx = torch.empty_like(gc)
+        want = xlow is not None
+        gwr = gwi = gb = ws = None
+        ws_bytes = 0
+        if want:
+            flat = torch.empty(2 * D * Fn + D, dtype=torch.float32, device=gc.device)
+            gwr, gwi, gb = flat[: D * Fn].view(D, Fn), flat[D * Fn: 2 * D * Fn].view(D, Fn), flat[2 * D * Fn:]
+            ws_bytes = _shape_info(B, T, D, Fn, io)[2]
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gc.device)
+        with _on_device(gc.device):
+            _native.check(lib.sml_backward(_ptr(gc), _ptr(xlow), _ptr(wr), _ptr(wi), _ptr(gx), _ptr(gwr), _ptr(gwi), _ptr(gb), _ptr(ws),
+                                           ws_bytes, B, T, D, Fn, io, _stream_handle(gc.device)))
+        need = ctx.needs_input_grad
+        dt = ctx.dtypes
+        return ((gx + gc) if need[0] else None,
+                gwr.to(dt[1]) if (want and need[1]) else None,
+                gwi.to(dt[2]) if (want and need[2]) else None,
+                gb.to(dt[3]) if (want and need[3]) else None)
+
+
+def spectral_mix_residual(x: torch.Tensor, layer: "SpectralMixingLayer") -> torch.Tensor:
+    """``x + layer(x)`` with the skip connection fused into the kernel's store (callers test ``fused_residual_supported``)."""
+    return _SpectralResidualFn.apply(x, layer.weight_real, layer.weight_imag, layer.bias)
+
+
+def fused_residual_supported(x: torch.Tensor, layer: "SpectralMixingLayer") -> bool:
+    if not (x.is_cuda and x.dim() == 3 and x.dtype in _IO_DTYPES and x.numel() > 0):
+        return False
+    if not (layer.learnable and layer.weight_real is not None) or (layer.training and layer.dropout.p > 0.0):
+        return False
+    if getattr(layer, "_grad_bucket", None) is not None:
+        return False
+    B, T, D = x.shape
+    return _ext_supported(B, T, D, layer.weight_real.shape[1], _IO_DTYPES[x.dtype])
+
+
 def ln_spectral_mix_residual(x: torch.Tensor, norm: nn.LayerNorm, layer: "SpectralMixingLayer") -> torch.Tensor:
     """``x + layer(norm(x))`` through the fused LayerNorm-on-load / residual-on-store kernel; raises if the shape is not
     one the extended kernels take (callers test ``fused_block_supported`` first)."""
@@ -472,8 +545,10 @@ class HybridSpectralAttention(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, T, D = x.shape
         H = self.num_heads
-        global_context = self.spectral(x)
-        qkv = self.qkv(self.norm(x + global_context)).reshape(B, T, 3, H, D // H).permute(2, 0, 3, 1, 4)
+        # x + global_context (spectral_layers.py:243-248): the skip connection rides on the fused kernel's store where the extended
+        # kernels take the shape and dropout is inactive
+        mixed = spectral_mix_residual(x, self.spectral) if fused_residual_supported(x, self.spectral) else x + self.spectral(x)
+        qkv = self.qkv(self.norm(mixed)).reshape(B, T, 3, H, D // H).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
         attn = F.softmax((q @ k.transpose(-2, -1)) / math.sqrt(D // H), dim=-1)
         attn = self.dropout(attn)

@@ -446,6 +446,8 @@ def test_hybrid_attention_golden(pkg, dev, golden_dir):
     mod.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}, strict=True)
     mod = mod.to(dev)
     x = torch.from_numpy(z["x"]).to(dev).requires_grad_(True)
+    from tensor_cuda_fft_b200 import spectral_layers as sl
+    assert sl.fused_residual_supported(x, mod.spectral)      # the skip connection x + global_context rides on the kernel's store
     y = mod(x)
     y.backward(torch.from_numpy(z["g"]).to(dev))
     torch.cuda.synchronize()
