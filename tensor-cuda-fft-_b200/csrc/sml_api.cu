@@ -47,6 +47,7 @@ const Knobs& knobs() {
         if (const char* e = getenv("SML_PDL")) v.pdl = atoi(e);   // 1: every kernel of the chain; 2: only the small batch-reduction kernel
         if (const char* e = getenv("SML_EXT_CTAS")) v.ext_ctas = atoi(e);
         if (const char* e = getenv("SML_SPLIT")) v.split = atoi(e);
+        if (const char* e = getenv("SML_L2_HINT")) v.l2_hint = atoi(e) != 0 ? 1 : 0;
         return v;
     }();
     return k;
@@ -385,6 +386,7 @@ int forward_impl(const void* x, const float* w_re, const float* w_im, const floa
         prm.ntiles = B * prm.ntd;
         prm.invT = invT;
         prm.dbg = debug_record();
+        prm.l2_hint = knobs().l2_hint;
         auto run = [&](const Plan& q) -> int {
             sml::FastParams pq = prm;
             const int slots = st->sm_count * q.ctas_per_sm;
@@ -488,6 +490,7 @@ int backward_impl(const void* g, const void* xlow, const float* w_re, const floa
         prm.ntiles = B * prm.ntd;
         prm.invT = invT;
         prm.dbg = debug_record();
+        prm.l2_hint = knobs().l2_hint;
         auto run = [&](const Plan& q) -> int {
             sml::FastParams pq = prm;
             const int slots = st->sm_count * q.ctas_per_sm;
@@ -610,6 +613,7 @@ int ext_impl(const void* in, const float* w_re, const float* w_im, const float* 
     prm.ntiles = B * prm.ntd;
     prm.invT = 1.0f / (float)T;
     prm.dbg = debug_record();
+        prm.l2_hint = knobs().l2_hint;
     prm.stats = (!BWD && e) ? reinterpret_cast<const float2*>(e->row_stats) : nullptr;
     prm.scale = e ? e->chan_scale : nullptr;
     prm.wnyq = e ? e->w_nyq : nullptr;

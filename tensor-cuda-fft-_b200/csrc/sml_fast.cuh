@@ -54,6 +54,7 @@ struct FastParams {
     unsigned int* dbg;     // host-mapped debug record (null unless SML_DEBUG is set): filled by a timed-out mbarrier wait
     // ---- pass splitting: `split` CTAs share one work item, each streams R / split consecutive passes; the partial bands meet in
     //      `xch` (one [2 KJ][threads] complex block per unit, L2-resident) and are summed by every CTA of the group in a fixed order
+    int l2_hint;           // 1: TMA loads / stores carry an L2 evict_first policy (tuning knob SML_L2_HINT)
     int split;             // 1 = off
     cf* xch;               // (ntiles * split) partial bands
     unsigned int* xflag;   // (ntiles) arrival counters, zero before the launch
@@ -165,6 +166,26 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, const void
     asm volatile(
         "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
         ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// the same with an L2 eviction-priority hint (createpolicy): activations are streamed once, evict_first keeps them from displacing
+// the filter rows / saved spectra that ARE re-used
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_4d_hint(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap* tmap, const void* src, int c0, int c1, int c2, int c3, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+        ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
         : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -634,9 +655,16 @@ __global__ void __launch_bounds__(NR* P, MINB)
         mbar_arrive(mbar + xslot(L));
 #else
         mbar_expect_tx(mbar + xslot(L), C::LOAD_BYTES);
+        if (prm.l2_hint) {
+            const uint64_t pol = l2_policy_evict_first();
 #pragma unroll
-        for (int bx = 0; bx < C::NBOX; ++bx)
-            tma_load_4d(xbuf(L) + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), tm, mbar + xslot(L), dt * 2 * P, rs, bx * C::BOXROWS - mshift, b);
+            for (int bx = 0; bx < C::NBOX; ++bx)
+                tma_load_4d_hint(xbuf(L) + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), tm, mbar + xslot(L), dt * 2 * P, rs, bx * C::BOXROWS - mshift, b, pol);
+        } else {
+#pragma unroll
+            for (int bx = 0; bx < C::NBOX; ++bx)
+                tma_load_4d(xbuf(L) + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), tm, mbar + xslot(L), dt * 2 * P, rs, bx * C::BOXROWS - mshift, b);
+        }
 #endif
     };
     // (stores are never shifted: TMA tensor stores fault on negative coordinates -- measured -- so an output window that
@@ -645,9 +673,16 @@ __global__ void __launch_bounds__(NR* P, MINB)
 #ifdef SML_DIAG_NO_STORE
         if (r >= 0) return;
 #endif
+        if (prm.l2_hint) {
+            const uint64_t pol = l2_policy_evict_first();
 #pragma unroll
-        for (int bx = 0; bx < C::NBOX; ++bx)
-            tma_store_4d(&tmap_out, stage + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), dt * 2 * P, r, bx * C::BOXROWS, b);
+            for (int bx = 0; bx < C::NBOX; ++bx)
+                tma_store_4d_hint(&tmap_out, stage + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), dt * 2 * P, r, bx * C::BOXROWS, b, pol);
+        } else {
+#pragma unroll
+            for (int bx = 0; bx < C::NBOX; ++bx)
+                tma_store_4d(&tmap_out, stage + (size_t)bx * C::BOXROWS * 2 * P * sizeof(IO), dt * 2 * P, r, bx * C::BOXROWS, b);
+        }
         tma_store_commit();
     };
     // uniform twiddle of pass r for band column j = tid (threads < NJ): W_T^{NR r f2s}, f2s = j (j < KJ) or j - NJ

@@ -25,6 +25,7 @@ struct Knobs {
     int fast_ctas = 0;   // 2 or 3: CTAs per SM of the NR = 32, KJ = 12 kernel (0 = default)
     int fast_xb = 0;     // 1 or 2: TMA landing tiles (0 = default)
     int tc = -1;         // 0 / 1: tensor-core kernel for eligible bf16 problems (-1 = default)
+    int l2_hint = 0;     // SML_L2_HINT=1: evict_first L2 policy on the TMA loads / stores of the activations
     int split = 0;       // SML_SPLIT: CTAs per work item of the pass-splitting schedule (0 = choose by the fill of the grid, 1 = off)
     int ext_ctas = 0;    // 2 or 3: CTAs per SM of the extended NR = 32, KJ <= 12 kernels (0 = default)
     int pdl = 0;         // SML_PDL=1: launch with programmatic dependent launch (measured slower inside the fwd/bwd/reduce chain: off by default)
