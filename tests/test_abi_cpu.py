@@ -131,3 +131,24 @@ def test_ext_plan_checks_without_gpu():
     assert ok(2, 2048, 64, 1024, T_in=1023, T_out=1024) != 0 and b"multiples of R" in lib.sml_last_error()
     assert ok(2, 2048, 64, 1024, T_in=1024, T_out=512, out_row0=4) != 0 and b"out_row0" in lib.sml_last_error()
     assert ok(2, 2048, 64, 1024, T_in=2000, in_row0=100) != 0              # window does not fit the transform
+
+
+def test_sml_ext_struct_matches_header():
+    """The ctypes mirror of sml_ext (_native.SmlExt) has the header's fields in the header's order with matching kinds."""
+    import ctypes
+    import re
+    from tensor_cuda_fft_b200 import _native as native
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "spectral_mix_b200.h")).read()
+    body = hdr[hdr.index("typedef struct sml_ext {"): hdr.index("} sml_ext;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        m = re.match(r"(const\s+)?(void|float|int)\s*(\*?)\s*(.+)$", decl)
+        assert m, decl
+        for name in m.group(4).split(","):
+            fields.append((name.strip().lstrip("*").strip(), "ptr" if m.group(3) == "*" or name.strip().startswith("*") else m.group(2)))
+    mirror = [(n, "ptr" if t is ctypes.c_void_p else ("int" if t is ctypes.c_int else "float")) for n, t in native.SmlExt._fields_]
+    assert fields == mirror
