@@ -20,7 +20,10 @@ One JSON line on stdout (rank 0):
   e2e          same metric through the C-ABI host-buffer call sml_fwd_bwd_host: HOST (pinned) x and g copied in and y, gx
                and the filter gradients copied back inside the timed region (chunked copy/compute pipeline)
   roofline     dominant kernel (fused backward): algorithmic bytes / measured launch time vs MEASURED_PEAKS.json
-  cpu_baseline oracle torch port (same torch.fft algorithm as the reference) timed on this box's host cores
+  cpu_baseline the unmodified reference module (baseline/_ref; oracle port if absent) timed on this box's host cores, bounded sample
+  sub-records of the default line (N = 1): bf16 (bf16 I/O of the same config), blocks (SpectralMLPBlock's
+               spectral half fused vs unfused, FixedSpectralBlock's half eager and graphed), graphed (launch-bound shapes:
+               fwd+bwd replayed from CUDA graphs, and the whole step as ONE graph), reference_algorithm_on_gpu (context)
 """
 from __future__ import annotations
 
